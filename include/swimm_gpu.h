@@ -1,0 +1,118 @@
+/*
+ * swimm_gpu.h -- C ABI of libswimm_cuda.so, the B200 (sm_100a) replacement for SWIMM's search kernels.
+ *
+ * What it replaces in the reference (enzorucci/SWIMM v1.1.3):
+ *   cpu_search_avx2_sp() / cpu_search_sse_sp()   CPUsearch.h:32-39, CPUsearch.c:6-967   (called from swimm.c:66-76)
+ *   assemble_single_chunk_db()'s lane interleave sequences.c:618-734                    (now a device-side layout build)
+ *   sort_scores() + the top-r print loop         utils.c:3-86, swimm.c:150-160          (now a device-side top-r)
+ *
+ * Conventions: plain C, plain pointers and sizes, caller owns every host buffer, the library owns
+ * all device memory.  Every function returns 0 on success and a negative swg_status otherwise; the
+ * library never calls exit().  There is NO CPU fallback: without a CUDA device every entry point
+ * that computes returns SWG_ERR_NO_DEVICE / SWG_ERR_CUDA.
+ *
+ * Residues are the reference's preprocessed codes (sequences.c:165-175): 0..22 = ABCDEFGHIKLMNPQRSTVWXYZ,
+ * 23 = dummy (J/O/U).  Database arrays are exactly the contents of <db>.seq: `lengths` ascending
+ * (stable), `residues` concatenated in that order.  A database index in any result is the position
+ * in that length-sorted order, i.e. the line number in <db>.desc -- the same index the reference's
+ * `scores` array uses (CPUsearch.c:548).
+ */
+#ifndef SWIMM_GPU_H
+#define SWIMM_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct swg_ctx swg_ctx;
+
+typedef enum {
+    SWG_OK = 0,
+    SWG_ERR_NO_DEVICE = -1,
+    SWG_ERR_CUDA = -2,
+    SWG_ERR_ARG = -3,
+    SWG_ERR_STATE = -4,
+    SWG_ERR_NOMEM = -5
+} swg_status;
+
+/* key of one hit: (uint32 score << 32) | database index; larger key = earlier in the hit list.
+ * This reproduces the reference order exactly: score descending, then index descending
+ * (utils.c:12 strict '>' in the merge, utils.c:52 '<=' swap). */
+#define SWG_KEY(score, index) (((uint64_t)(uint32_t)(score) << 32) | (uint64_t)(uint32_t)(index))
+#define SWG_KEY_SCORE(key)    ((int32_t)((key) >> 32))
+#define SWG_KEY_INDEX(key)    ((uint64_t)((key) & 0xffffffffu))
+
+typedef struct {
+    double device_seconds;     /* CUDA-event time of the last run: profile build + all search kernels (+ top-r) */
+    double search_seconds;     /* the part of it spent in the alignment kernels (the reference's workTime region) */
+    double topr_seconds;       /* the part spent in top-r selection */
+    uint64_t cells;            /* sum over queries of query_length * local database residues */
+    uint64_t padded_cells;     /* cell updates actually executed (tile padding, pipeline fill, lane pairing) */
+    uint64_t launches;         /* kernels launched by the last run */
+    uint64_t rescored;         /* (query, sequence) pairs that left the 16-bit range and were redone in 32 bits */
+    uint64_t db_bytes;         /* bytes of the resident tiled database on this device */
+    uint64_t h2d_bytes;        /* host->device bytes of the last search call */
+    uint64_t d2h_bytes;        /* device->host bytes of the last search call */
+} swg_stats;
+
+/* ---- context ---- */
+int swg_gpu_device_count(int *count);
+int swg_gpu_create(int device, swg_ctx **ctx);                 /* one context per GPU (per process or per host thread) */
+void swg_gpu_destroy(swg_ctx *ctx);
+const char *swg_gpu_last_error(const swg_ctx *ctx);           /* static string when ctx == NULL */
+
+/* ---- database (replaces assemble_single_chunk_db, sequences.c:618-734) ----
+ * Uploads the flat database and builds the tiled, pair-interleaved device layout on the GPU.
+ * shard/num_shards: this context keeps tiles (16 consecutive sorted sequences) t with
+ * t % num_shards == shard, so every shard gets the same residue count and length mix. */
+int swg_gpu_load_db(swg_ctx *ctx, const uint16_t *lengths, const signed char *residues,
+                    uint64_t n_sequences, uint64_t n_residues, int shard, int num_shards);
+/* same, from the reference's 32- or 16-lane interleaved arrays (what swimm.c:74-76 hands to
+ * cpu_search_avx2_sp): vect_db[disp[g] + j*vector_length + k], padded with code 24. */
+int swg_gpu_load_db_interleaved(swg_ctx *ctx, const signed char *vect_db, const uint16_t *vect_lengths,
+                                uint64_t vect_count, const uint64_t *vect_disp, int vector_length,
+                                uint64_t n_sequences, int shard, int num_shards);
+uint64_t swg_gpu_db_local_sequences(const swg_ctx *ctx);
+uint64_t swg_gpu_db_local_residues(const swg_ctx *ctx);
+
+/* ---- search (replaces cpu_search_avx2_sp + sort_scores) ----
+ * queries:    residue codes, concatenated; query i is queries[q_disp[i] .. q_disp[i] + q_lengths[i])
+ * q_lengths:  REAL lengths (no even padding needed; a trailing dummy residue is harmless)
+ * submat:     24x32 signed bytes, row = query code, column = database code (reference submat.c)
+ * top:        hits per query wanted (clamped to n_sequences)
+ * scores:     NULL, or [q_count][n_sequences] int32 -- entries of sequences this shard holds are written
+ * top_keys:   NULL, or [q_count][top] SWG_KEYs of this shard's best hits, descending, padded with 0
+ * work_seconds: NULL, or receives swg_stats.search_seconds (the reference's *workTime) */
+int swg_gpu_search(swg_ctx *ctx, const signed char *queries, const uint16_t *q_lengths, const uint32_t *q_disp,
+                   uint64_t q_count, const signed char *submat, int open_gap, int extend_gap, uint64_t top,
+                   int32_t *scores, uint64_t *top_keys, double *work_seconds);
+
+/* the same call in three steps, so that several GPUs can be driven from one host thread and so
+ * that the kernels can be timed with the inputs already resident in HBM */
+int swg_gpu_set_queries(swg_ctx *ctx, const signed char *queries, const uint16_t *q_lengths, const uint32_t *q_disp,
+                        uint64_t q_count, const signed char *submat, int open_gap, int extend_gap);   /* H2D */
+int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores);     /* enqueue all kernels; returns immediately */
+int swg_gpu_fetch(swg_ctx *ctx, int32_t *scores, uint64_t *top_keys);   /* wait + D2H */
+int swg_gpu_sync(swg_ctx *ctx);                                   /* wait only */
+
+int swg_gpu_get_stats(swg_ctx *ctx, swg_stats *out);
+
+/* tuning knobs (all optional): name in {"long_threshold", "force_group", "force_rows", "block_threads"} */
+int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value);
+
+/* Drop-in with the reference signature (CPUsearch.h:37-39).  n_threads is read as the number of GPUs
+ * to use (0 = all), cpu_block_size is ignored.  Fills scores[q*vect_count*vector_length + s] for every
+ * lane (padded lanes get 0) and *workTime, exactly as cpu_search_avx2_sp does.  vector_length is 32. */
+int swimm_gpu_search_avx2_compat(char *query_sequences, unsigned short int *query_sequences_lengths,
+                                 unsigned long int query_sequences_count, unsigned int *query_disp,
+                                 char *vect_sequences_db, unsigned short int *vect_sequences_db_lengths,
+                                 unsigned short int *vect_sequences_db_blocks, unsigned long int vect_sequences_db_count,
+                                 unsigned long int *vect_sequences_db_disp, char *submat, int open_gap, int extend_gap,
+                                 int n_threads, int cpu_block_size, int *scores, double *workTime);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,101 @@
+// swg_common.cuh -- shared constants, parameter blocks and lane policies of the sm_100a search kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace swg {
+
+// ---- device database layout --------------------------------------------------------------------
+// Sorted sequences are grouped 16 to a TILE (8 PAIRS).  All 16 are padded to the tile's column
+// count (a multiple of 8).  Columns are stored in CHUNKS of 8: one 16-byte unit per (chunk, pair)
+//     unit(tile, chunk, pair) = tile_off[tile] + chunk * 8 + pair            (16-byte units)
+//     byte 2*c + 0 = residue of sequence 2*pair   at column 8*chunk + c,  byte 2*c + 1 = sequence 2*pair+1
+// so one 32-bit word holds two columns of a pair and the 8 pairs of a chunk are 128 contiguous
+// bytes (a warp's groups read neighbouring units).  Residues are stored as code*4 so that a byte
+// placed in byte lane 1 of a register is directly the profile offset code*1024 (one PRMT).
+constexpr int kTileSeqs = 16;
+constexpr int kTilePairs = 8;
+constexpr int kChunkCols = 8;
+constexpr int kPadCode = 24;                 // reference sequences.h:17
+constexpr uint32_t kPadWord = 0x60606060u;   // four pad residues (24*4)
+
+// ---- query profile layout (global and shared memory, identical) -----------------------------------
+// profile[pass][letter 0..24][1024 bytes]; inside a letter row, for a group of G threads with K rows each:
+//     row x of thread t  ->  (x / 16) * (G * 16) + t * 16 + (x % 16)
+// i.e. 16-row chunks, thread-interleaved: the quarter-warp of an LDS.128 covers 8 consecutive threads
+// -> 8 distinct 16-byte bank groups, conflict-free for G >= 8 whatever letters the threads look up.
+constexpr int kLetters = 25;
+constexpr int kLetterStride = 1024;
+constexpr int kPassBytes = kLetters * kLetterStride;
+constexpr int kMaxRowsPerThread = 32;
+constexpr int kMaxPassRows = 1024;           // 32 threads x 32 rows
+
+constexpr int kBlockThreads = 512;
+constexpr int kOverflow16 = 32000;           // a 16-bit lane whose best reaches this is redone in 32 bits
+
+struct WfParams {
+    const uint4 *db;              // tiled database, 16-byte units
+    const uint64_t *tile_off;     // [ntiles + 1] in 16-byte units
+    const uint32_t *tile_cols;    // [ntiles] padded column count (multiple of 8)
+    uint32_t ntiles;              // local tiles
+    uint32_t tile_first, tile_count;   // sub-range of tiles this launch covers (longest-first inside it)
+    uint64_t n_total;             // sequences in the whole database (all shards)
+    uint32_t shard, num_shards;
+    const uint8_t *profile;       // [passes][25][1024]
+    uint32_t passes;
+    int32_t *scores;              // [ntiles * 16] local scores of the current query
+    uint2 *boundary;              // [resident warps][maxcols] last-row (H, F) between passes
+    uint32_t maxcols;
+    uint32_t *task_counter;
+    uint32_t *resc_count;         // number of entries in resc_list
+    uint32_t *resc_list;          // local sequence ids to redo in 32 bits
+    int gap_open_extend;          // go + ge
+    int gap_extend;               // ge
+};
+
+__device__ __forceinline__ uint64_t global_seq_index(const WfParams &p, uint32_t local_seq)
+{
+    const uint32_t ltile = local_seq / kTileSeqs;
+    return ((uint64_t)ltile * p.num_shards + p.shard) * kTileSeqs + (local_seq % kTileSeqs);
+}
+
+// ---- lane policies ---------------------------------------------------------------------------------
+// Lane16: two database sequences per thread group in the halves of a 32-bit register (s16x2 DPX).
+// Lane32: one sequence per group, plain int32 DPX -- the exact re-computation of overflowed lanes.
+struct Lane16 {
+    static constexpr int kSeqs = 2;
+    typedef uint32_t reg;
+    static __device__ __forceinline__ reg splat(int v) { return (uint32_t)(v & 0xffff) * 0x10001u; }
+    static __device__ __forceinline__ reg addmax(reg a, reg b, reg c) { return __viaddmax_s16x2(a, b, c); }
+    static __device__ __forceinline__ reg max_relu(reg a, reg b) { return __vimax_s16x2_relu(a, b); }
+    static __device__ __forceinline__ reg add(reg a, reg b) { return __vadd2(a, b); }
+    static __device__ __forceinline__ reg max2(reg a, reg b) { return __vmaxs2(a, b); }
+    static __device__ __forceinline__ reg max3(reg a, reg b, reg c) { return __vimax3_s16x2(a, b, c); }
+    // substitution scores of row byte B for the two sequences: {sext16(w_hi.b[B]), sext16(w_lo.b[B])}
+    template <int B>
+    static __device__ __forceinline__ reg score(uint32_t w_lo, uint32_t w_hi)
+    {
+        constexpr uint32_t sel = (uint32_t)B | ((8u | B) << 4) | ((4u + B) << 8) | ((12u + B) << 12);
+        return __byte_perm(w_lo, w_hi, sel);
+    }
+};
+
+struct Lane32 {
+    static constexpr int kSeqs = 1;
+    typedef int32_t reg;
+    static __device__ __forceinline__ reg splat(int v) { return v; }
+    static __device__ __forceinline__ reg addmax(reg a, reg b, reg c) { return __viaddmax_s32(a, b, c); }
+    static __device__ __forceinline__ reg max_relu(reg a, reg b) { return __vimax_s32_relu(a, b); }
+    static __device__ __forceinline__ reg add(reg a, reg b) { return a + b; }
+    static __device__ __forceinline__ reg max2(reg a, reg b) { return max(a, b); }
+    static __device__ __forceinline__ reg max3(reg a, reg b, reg c) { return __vimax3_s32(a, b, c); }
+    template <int B>
+    static __device__ __forceinline__ reg score(uint32_t w_lo, uint32_t)
+    {
+        constexpr uint32_t sel = (uint32_t)B | ((8u | B) << 4) | ((8u | B) << 8) | ((8u | B) << 12);
+        return (int32_t)__byte_perm(w_lo, 0u, sel);
+    }
+};
+
+}  // namespace swg
