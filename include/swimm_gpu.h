@@ -69,6 +69,10 @@ const char *swg_gpu_last_error(const swg_ctx *ctx);           /* static string w
  * t % num_shards == shard, so every shard gets the same residue count and length mix. */
 int swg_gpu_load_db(swg_ctx *ctx, const uint16_t *lengths, const signed char *residues,
                     uint64_t n_sequences, uint64_t n_residues, int shard, int num_shards);
+/* same, when the caller holds only this shard's sequences (tiles shard, shard+num_shards, ... of the whole
+ * length-sorted database, back to back): what one process per GPU loads in a multi-GPU job. */
+int swg_gpu_load_db_shard(swg_ctx *ctx, const uint16_t *local_lengths, const signed char *local_residues,
+                          uint64_t n_local, uint64_t n_local_residues, int shard, int num_shards, uint64_t n_total);
 /* same, from the reference's 32- or 16-lane interleaved arrays (what swimm.c:74-76 hands to
  * cpu_search_avx2_sp): vect_db[disp[g] + j*vector_length + k], padded with code 24. */
 int swg_gpu_load_db_interleaved(swg_ctx *ctx, const signed char *vect_db, const uint16_t *vect_lengths,
@@ -81,9 +85,9 @@ uint64_t swg_gpu_db_local_residues(const swg_ctx *ctx);
  * queries:    residue codes, concatenated; query i is queries[q_disp[i] .. q_disp[i] + q_lengths[i])
  * q_lengths:  REAL lengths (no even padding needed; a trailing dummy residue is harmless)
  * submat:     24x32 signed bytes, row = query code, column = database code (reference submat.c)
- * top:        hits per query wanted (clamped to n_sequences)
+ * top:        hits per query wanted; only min(top, n_sequences) exist (reference swimm.c:51)
  * scores:     NULL, or [q_count][n_sequences] int32 -- entries of sequences this shard holds are written
- * top_keys:   NULL, or [q_count][top] SWG_KEYs of this shard's best hits, descending, padded with 0
+ * top_keys:   NULL, or [q_count][top] SWG_KEYs of this shard's best hits, descending, rows padded with 0
  * work_seconds: NULL, or receives swg_stats.search_seconds (the reference's *workTime) */
 int swg_gpu_search(swg_ctx *ctx, const signed char *queries, const uint16_t *q_lengths, const uint32_t *q_disp,
                    uint64_t q_count, const signed char *submat, int open_gap, int extend_gap, uint64_t top,
@@ -98,6 +102,12 @@ int swg_gpu_fetch(swg_ctx *ctx, int32_t *scores, uint64_t *top_keys);   /* wait 
 int swg_gpu_sync(swg_ctx *ctx);                                   /* wait only */
 
 int swg_gpu_get_stats(swg_ctx *ctx, swg_stats *out);
+
+/* Measured issue rates of the search kernel's instruction mix (the integer roofline the search is
+ * reported against).  ginstr_per_s[p] = 1e9 thread-instructions per second on the whole GPU for probe p,
+ * sm_mhz[p] = the SM clock during it, names[p] = static strings.  max_probes >= 32 is enough. */
+int swg_gpu_pipebench(swg_ctx *ctx, int max_probes, double *ginstr_per_s, double *sm_mhz, const char **names,
+                      int *n_probes, int *sm_count);
 
 /* tuning knobs (all optional): name in {"long_threshold", "force_group", "force_rows", "block_threads"} */
 int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value);

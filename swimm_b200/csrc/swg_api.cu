@@ -1,0 +1,826 @@
+// swg_api.cu -- the C ABI of libswimm_cuda.so (include/swimm_gpu.h): context, resident database,
+// query upload, kernel scheduling, top-r, statistics, and the reference-signature entry point.
+//
+// One context drives one GPU through one stream.  A search call enqueues, per query,
+//     profile build (K0)  ->  [long tiles: wavefront<Lane16, 32, KL>]  ->  wavefront<Lane16, G, K>  (K1)
+//                         ->  wavefront<Lane32, 32, KL> over the lanes that left the 16-bit range  (K2)
+// and once per batch the top-r selection (K4); nothing waits on the host until the results are fetched.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/swimm_gpu.h"
+#include "swg_internal.h"
+#include "wavefront.cuh"
+
+using namespace swg;
+
+namespace {
+
+constexpr int kMaxSmemPasses = 8;            // 8 x 25 KB of query profile per CTA
+constexpr uint32_t kDefaultLongCols = 3072;  // tiles with more columns than this go to the 32-thread kernel
+
+struct Config {          // how one query is mapped onto thread groups
+    int G, K;
+    uint32_t passes;
+    bool global_profile;
+};
+
+struct DeviceBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct swg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_search_end = nullptr, ev_end = nullptr;
+    char err[512] = {0};
+
+    // resident database shard
+    bool db_ready = false;
+    uint64_t n_total = 0;            // sequences of the whole database
+    uint32_t shard = 0, num_shards = 1;
+    uint32_t ntiles = 0;             // local tiles
+    uint32_t first_long_tile = 0;    // local tiles [first_long_tile, ntiles) have more than long_cols columns
+    uint64_t local_seqs = 0, local_residues = 0, db_units = 0;
+    uint32_t maxcols = 8;
+    double avg_cols = 8;
+    std::vector<uint32_t> h_tile_cols;
+    DeviceBuf d_db, d_tile_off, d_tile_cols;
+
+    // queries of the current batch
+    bool queries_ready = false;
+    uint64_t q_count = 0;
+    std::vector<uint16_t> q_len;
+    std::vector<uint32_t> q_off;     // offsets into d_queries
+    int open_gap = 10, extend_gap = 2;
+    DeviceBuf d_queries, d_submat;
+
+    // work buffers
+    DeviceBuf d_scores, d_profile, d_profile32, d_boundary, d_counters, d_resc_list, d_topk_scratch, d_top_out;
+    std::vector<uint32_t> h_counters;
+    uint64_t run_top = 0, run_top_stride = 0;
+    bool run_done = false, run_kept_scores = false;
+
+    // options
+    long long_cols = kDefaultLongCols;
+    long force_group = 0, force_rows = 0;
+
+    swg_stats stats;
+};
+
+namespace {
+
+const char *status_text(int st)
+{
+    switch (st) {
+        case SWG_OK: return "ok";
+        case SWG_ERR_NO_DEVICE: return "no CUDA device";
+        case SWG_ERR_CUDA: return "CUDA error";
+        case SWG_ERR_ARG: return "bad argument";
+        case SWG_ERR_STATE: return "call out of order";
+        case SWG_ERR_NOMEM: return "out of memory";
+        default: return "unknown";
+    }
+}
+
+char g_last_error[512] = "no error";
+
+int fail(swg_ctx *ctx, int st, const char *fmt, ...)
+{
+    char buf[400];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    snprintf(g_last_error, sizeof(g_last_error), "%s: %s", status_text(st), buf);
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", status_text(st), buf);
+    return st;
+}
+
+int cuda_fail(swg_ctx *ctx, cudaError_t e, const char *what)
+{
+    const int st = (e == cudaErrorMemoryAllocation) ? SWG_ERR_NOMEM
+                   : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SWG_ERR_NO_DEVICE
+                                                                                  : SWG_ERR_CUDA;
+    return fail(ctx, st, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define SWG_CUDA(ctx, call)                                         \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);  \
+    } while (0)
+
+// ---- mapping a query onto thread groups ---------------------------------------------------------
+// Cost model (relative time per database column): the group computes passes * G * K rows of which m are
+// useful, every column step costs about kStepOverhead rows of bookkeeping (shuffles, profile fetch, loop),
+// and a sequence of L columns occupies the systolic pipeline for L + G - 1 steps.
+constexpr double kStepOverhead = 3.0;
+
+double config_cost(uint32_t m, int G, int K, uint32_t passes, double avg_cols)
+{
+    double c = (double)passes * G * (K + kStepOverhead) * (avg_cols + G - 1) / avg_cols;
+    if (G == 4) c *= 1.15;          // two groups share a quarter-warp: profile reads conflict 2-way
+    (void)m;
+    return c;
+}
+
+Config choose_config(uint32_t m, double avg_cols, long force_group, long force_rows)
+{
+    Config best = {32, 32, 1, false};
+    if (m == 0) m = 1;
+    double best_cost = 1e300;
+    for (int G = 4; G <= 32; G *= 2) {
+        if (force_group && G != force_group) continue;
+        for (int K = 1; K <= kMaxRowsPerThread; ++K) {
+            if (force_rows && K != force_rows) continue;
+            const uint32_t rows = (uint32_t)(G * K);
+            const uint32_t passes = (m + rows - 1) / rows;
+            if (passes > 1 && G != 32) continue;     // the pass boundary line is per warp: one pair per warp
+            const double c = config_cost(m, G, K, passes, avg_cols);
+            if (c < best_cost) { best_cost = c; best = {G, K, passes, passes > (uint32_t)kMaxSmemPasses}; }
+        }
+    }
+    if (best_cost == 1e300) {       // forced values that cannot hold the query: fall back to the widest shape
+        const uint32_t passes = (m + 1023) / 1024;
+        best = {32, 32, passes, passes > (uint32_t)kMaxSmemPasses};
+    }
+    if (best.global_profile) { best.G = 32; best.K = 32; best.passes = (m + 1023) / 1024; }
+    return best;
+}
+
+// the 32-thread shape used for long tiles and for the 32-bit re-computation
+Config wide_config(uint32_t m)
+{
+    if (m == 0) m = 1;
+    Config c;
+    c.G = 32;
+    if (m <= 1024) { c.K = (int)((m + 31) / 32); c.passes = 1; }
+    else {
+        // fewest passes, then the fewest rows per thread that still cover the query
+        c.passes = (m + 1023) / 1024;
+        c.K = (int)((m + 32 * c.passes - 1) / (32 * c.passes));
+    }
+    c.global_profile = c.passes > (uint32_t)kMaxSmemPasses;
+    if (c.global_profile) c.K = 32;
+    return c;
+}
+
+cudaError_t launch_wavefront(bool lane32, const Config &cfg, int grid, cudaStream_t stream, const WfParams &p)
+{
+    if (cfg.global_profile) return lane32 ? launch_wf_l32_gp(grid, stream, p) : launch_wf_l16_gp(grid, stream, p);
+    const size_t smem = (size_t)cfg.passes * kPassBytes;
+    if (lane32) return launch_wf_l32_g32(cfg.K, grid, smem, stream, p);
+    switch (cfg.G) {
+        case 4: return launch_wf_l16_g4(cfg.K, grid, smem, stream, p);
+        case 8: return launch_wf_l16_g8(cfg.K, grid, smem, stream, p);
+        case 16: return launch_wf_l16_g16(cfg.K, grid, smem, stream, p);
+        case 32: return launch_wf_l16_g32(cfg.K, grid, smem, stream, p);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+void free_db(swg_ctx *c)
+{
+    c->d_db.release();
+    c->d_tile_off.release();
+    c->d_tile_cols.release();
+    c->db_ready = false;
+}
+
+// Shared tail of the two database loaders: `lengths`/`offsets` describe the LOCAL sequences (padded to a
+// multiple of 16 with zero-length entries), d_res holds their residues back to back.
+int finish_load(swg_ctx *ctx, const std::vector<uint16_t> &len, const std::vector<uint64_t> &off, const int8_t *d_res)
+{
+    const uint32_t ntiles = (uint32_t)(len.size() / kTileSeqs);
+    std::vector<uint64_t> tile_off(ntiles + 1, 0);
+    ctx->h_tile_cols.assign(ntiles, 0);
+    uint32_t maxcols = kChunkCols;
+    double sum_cols = 0;
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        uint32_t mx = 1;
+        for (int k = 0; k < kTileSeqs; ++k) mx = std::max<uint32_t>(mx, len[(size_t)t * kTileSeqs + k]);
+        const uint32_t cols = (mx + kChunkCols - 1) / kChunkCols * kChunkCols;
+        ctx->h_tile_cols[t] = cols;
+        tile_off[t + 1] = tile_off[t] + (uint64_t)(cols / kChunkCols) * kTilePairs;
+        maxcols = std::max(maxcols, cols);
+        sum_cols += cols;
+    }
+    ctx->ntiles = ntiles;
+    ctx->maxcols = maxcols;
+    ctx->avg_cols = ntiles ? sum_cols / ntiles : 8.0;
+    ctx->db_units = tile_off[ntiles];
+    uint32_t fl = ntiles;
+    while (fl > 0 && ctx->h_tile_cols[fl - 1] > (uint32_t)ctx->long_cols) --fl;   // lengths ascend: long tiles are last
+    ctx->first_long_tile = fl;
+
+    DeviceBuf d_off, d_len;
+    SWG_CUDA(ctx, ctx->d_db.reserve(std::max<uint64_t>(ctx->db_units, 1) * sizeof(uint4)));
+    SWG_CUDA(ctx, ctx->d_tile_off.reserve((ntiles + 1) * sizeof(uint64_t)));
+    SWG_CUDA(ctx, ctx->d_tile_cols.reserve(std::max<uint32_t>(ntiles, 1) * sizeof(uint32_t)));
+    SWG_CUDA(ctx, d_off.reserve(off.size() * sizeof(uint64_t)));
+    SWG_CUDA(ctx, d_len.reserve(std::max<size_t>(len.size(), 1) * sizeof(uint16_t)));
+    cudaError_t e = cudaMemcpyAsync(ctx->d_tile_off.p, tile_off.data(), (ntiles + 1) * sizeof(uint64_t),
+                                    cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && ntiles)
+        e = cudaMemcpyAsync(ctx->d_tile_cols.p, ctx->h_tile_cols.data(), ntiles * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                            ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_off.p, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && !len.empty())
+        e = cudaMemcpyAsync(d_len.p, len.data(), len.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = launch_build_tiles(d_res, d_off.as<uint64_t>(), d_len.as<uint16_t>(), ctx->d_tile_off.as<uint64_t>(), ntiles,
+                               ctx->db_units, ctx->d_db.as<uint4>(), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    d_off.release();
+    d_len.release();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "database layout build");
+    ctx->stats.db_bytes = ctx->db_units * sizeof(uint4);
+    ctx->db_ready = true;
+    ctx->run_done = false;
+    return SWG_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int swg_gpu_device_count(int *count)
+{
+    if (!count) return fail(nullptr, SWG_ERR_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return cuda_fail(nullptr, e, "cudaGetDeviceCount"); }
+    *count = n;
+    return n > 0 ? SWG_OK : fail(nullptr, SWG_ERR_NO_DEVICE, "no CUDA device visible");
+}
+
+int swg_gpu_create(int device, swg_ctx **out)
+{
+    if (!out) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceCount");
+    if (n <= 0) return fail(nullptr, SWG_ERR_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, SWG_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    swg_ctx *ctx = new (std::nothrow) swg_ctx();
+    if (!ctx) return fail(nullptr, SWG_ERR_NOMEM, "context");
+    ctx->device = device;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    e = cudaSetDevice(device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess && prop.major < 10) {
+        delete ctx;
+        return fail(nullptr, SWG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    }
+    if (e == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_begin);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_search_end);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_end);
+    if (e != cudaSuccess) {
+        const int st = cuda_fail(nullptr, e, "context creation");
+        delete ctx;
+        return st;
+    }
+    *out = ctx;
+    return SWG_OK;
+}
+
+void swg_gpu_destroy(swg_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_db(ctx);
+    ctx->d_queries.release();
+    ctx->d_submat.release();
+    ctx->d_scores.release();
+    ctx->d_profile.release();
+    ctx->d_profile32.release();
+    ctx->d_boundary.release();
+    ctx->d_counters.release();
+    ctx->d_resc_list.release();
+    ctx->d_topk_scratch.release();
+    ctx->d_top_out.release();
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_search_end) cudaEventDestroy(ctx->ev_search_end);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *swg_gpu_last_error(const swg_ctx *ctx) { return ctx ? ctx->err : g_last_error; }
+
+int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value)
+{
+    if (!ctx || !name) return fail(ctx, SWG_ERR_ARG, "NULL argument");
+    if (!strcmp(name, "long_threshold")) {
+        if (value < 8) return fail(ctx, SWG_ERR_ARG, "long_threshold must be >= 8");
+        ctx->long_cols = value;
+        if (ctx->db_ready) {
+            uint32_t fl = ctx->ntiles;
+            while (fl > 0 && ctx->h_tile_cols[fl - 1] > (uint32_t)value) --fl;
+            ctx->first_long_tile = fl;
+        }
+    } else if (!strcmp(name, "force_group")) {
+        if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32)
+            return fail(ctx, SWG_ERR_ARG, "force_group must be 0, 4, 8, 16 or 32");
+        ctx->force_group = value;
+    } else if (!strcmp(name, "force_rows")) {
+        if (value < 0 || value > kMaxRowsPerThread) return fail(ctx, SWG_ERR_ARG, "force_rows must be 0..32");
+        ctx->force_rows = value;
+    } else if (!strcmp(name, "block_threads")) {
+        if (value != kBlockThreads) return fail(ctx, SWG_ERR_ARG, "block_threads is fixed at %d in this build", kBlockThreads);
+    } else {
+        return fail(ctx, SWG_ERR_ARG, "unknown option '%s'", name);
+    }
+    return SWG_OK;
+}
+
+// ---- database ----------------------------------------------------------------------------------
+// Upload `local_res` bytes described by `len`/`off` (local sequences, padded to whole tiles) and build the layout.
+// src_of_tile[lt] = offset of local tile lt's first residue inside `residues` (NULL: the tiles are back to back).
+static int upload_and_build(swg_ctx *ctx, const std::vector<uint16_t> &len, const std::vector<uint64_t> &off,
+                            const signed char *residues, const uint64_t *src_of_tile)
+{
+    const uint64_t ltiles = len.size() / kTileSeqs;
+    const uint64_t local_res = off[len.size()];
+    DeviceBuf d_res;
+    SWG_CUDA(ctx, d_res.reserve(std::max<uint64_t>(local_res, 1)));
+    cudaError_t e = cudaSuccess;
+    if (!src_of_tile) {
+        if (local_res) e = cudaMemcpyAsync(d_res.p, residues, local_res, cudaMemcpyHostToDevice, ctx->stream);
+    } else {
+        // tile ranges gathered through two pinned staging buffers
+        const size_t kStage = 32u << 20;
+        char *stage[2] = {nullptr, nullptr};
+        cudaEvent_t done[2] = {nullptr, nullptr};
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+            e = cudaMallocHost((void **)&stage[b], kStage);
+            if (e == cudaSuccess) e = cudaEventCreate(&done[b]);
+        }
+        uint64_t lt = 0, dst = 0;
+        int b = 0;
+        while (e == cudaSuccess && lt < ltiles) {
+            e = cudaEventSynchronize(done[b]);          // a never-recorded event is complete
+            size_t fill = 0;
+            while (lt < ltiles) {
+                const uint64_t bytes = off[(lt + 1) * kTileSeqs] - off[lt * kTileSeqs];
+                if (bytes > kStage) { e = cudaErrorInvalidValue; break; }     // 16 x 65535 < 32 MiB: cannot happen
+                if (fill + bytes > kStage) break;
+                memcpy(stage[b] + fill, residues + src_of_tile[lt], bytes);
+                fill += bytes;
+                ++lt;
+            }
+            if (e == cudaSuccess && fill) {
+                e = cudaMemcpyAsync(d_res.as<char>() + dst, stage[b], fill, cudaMemcpyHostToDevice, ctx->stream);
+                if (e == cudaSuccess) e = cudaEventRecord(done[b], ctx->stream);
+                dst += fill;
+            }
+            b ^= 1;
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        for (int k = 0; k < 2; ++k) {
+            if (stage[k]) cudaFreeHost(stage[k]);
+            if (done[k]) cudaEventDestroy(done[k]);
+        }
+    }
+    if (e != cudaSuccess) { d_res.release(); return cuda_fail(ctx, e, "database upload"); }
+    const int st = finish_load(ctx, len, off, d_res.as<int8_t>());
+    d_res.release();
+    return st;
+}
+
+int swg_gpu_load_db(swg_ctx *ctx, const uint16_t *lengths, const signed char *residues, uint64_t n_sequences,
+                    uint64_t n_residues, int shard, int num_shards)
+{
+    if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
+    if (num_shards < 1 || shard < 0 || shard >= num_shards) return fail(ctx, SWG_ERR_ARG, "shard %d of %d", shard, num_shards);
+    if (n_sequences && (!lengths || (!residues && n_residues))) return fail(ctx, SWG_ERR_ARG, "NULL database arrays");
+    if (n_sequences >= (1ull << 32) - kTileSeqs) return fail(ctx, SWG_ERR_ARG, "more than 2^32 sequences");
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    free_db(ctx);
+    ctx->n_total = n_sequences;
+    ctx->shard = (uint32_t)shard;
+    ctx->num_shards = (uint32_t)num_shards;
+
+    // local tiles: global tile t (16 consecutive sorted sequences) belongs to shard t % num_shards
+    const uint64_t gtiles = (n_sequences + kTileSeqs - 1) / kTileSeqs;
+    const uint64_t ltiles = gtiles > (uint64_t)shard ? (gtiles - shard + num_shards - 1) / num_shards : 0;
+    std::vector<uint16_t> len(ltiles * kTileSeqs, 0);
+    std::vector<uint64_t> off(ltiles * kTileSeqs + 1, 0);
+    std::vector<uint64_t> tile_src(ltiles + 1, 0);   // where each local tile's residues start in the caller's array
+    {
+        uint64_t pos = 0, lt = 0;
+        for (uint64_t t = 0; t < gtiles; ++t) {
+            const bool mine = (t % num_shards) == (uint64_t)shard;
+            if (mine) tile_src[lt] = pos;
+            for (int k = 0; k < kTileSeqs; ++k) {
+                const uint64_t s = t * kTileSeqs + k;
+                const uint16_t l = s < n_sequences ? lengths[s] : 0;
+                if (mine) len[lt * kTileSeqs + k] = l;
+                pos += l;
+            }
+            if (mine) ++lt;
+        }
+        if (pos != n_residues) return fail(ctx, SWG_ERR_ARG, "lengths sum to %llu residues, caller said %llu",
+                                           (unsigned long long)pos, (unsigned long long)n_residues);
+    }
+    uint64_t local_res = 0, local_seqs = 0;
+    for (size_t i = 0; i < len.size(); ++i) {
+        off[i] = local_res;
+        local_res += len[i];
+    }
+    off[len.size()] = local_res;
+    for (uint64_t lt = 0; lt < ltiles; ++lt) {
+        const uint64_t g0 = (lt * num_shards + shard) * kTileSeqs;
+        local_seqs += std::min<uint64_t>(kTileSeqs, n_sequences - g0);
+    }
+    ctx->local_seqs = local_seqs;
+    ctx->local_residues = local_res;
+    return upload_and_build(ctx, len, off, residues, num_shards == 1 ? nullptr : tile_src.data());
+}
+
+int swg_gpu_load_db_shard(swg_ctx *ctx, const uint16_t *local_lengths, const signed char *local_residues,
+                          uint64_t n_local, uint64_t n_local_residues, int shard, int num_shards, uint64_t n_total)
+{
+    if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
+    if (num_shards < 1 || shard < 0 || shard >= num_shards) return fail(ctx, SWG_ERR_ARG, "shard %d of %d", shard, num_shards);
+    if (n_local && (!local_lengths || (!local_residues && n_local_residues))) return fail(ctx, SWG_ERR_ARG, "NULL database arrays");
+    if (n_total >= (1ull << 32) - kTileSeqs) return fail(ctx, SWG_ERR_ARG, "more than 2^32 sequences");
+    // the caller's sequences must be exactly the tiles t = shard, shard + num_shards, ... of the whole database
+    const uint64_t gtiles = (n_total + kTileSeqs - 1) / kTileSeqs;
+    const uint64_t ltiles = gtiles > (uint64_t)shard ? (gtiles - shard + num_shards - 1) / num_shards : 0;
+    uint64_t expect = 0;
+    for (uint64_t lt = 0; lt < ltiles; ++lt) {
+        const uint64_t g0 = (lt * num_shards + shard) * kTileSeqs;
+        expect += std::min<uint64_t>(kTileSeqs, n_total - g0);
+    }
+    if (expect != n_local)
+        return fail(ctx, SWG_ERR_ARG, "shard %d of %d of a %llu-sequence database holds %llu sequences, caller passed %llu",
+                    shard, num_shards, (unsigned long long)n_total, (unsigned long long)expect, (unsigned long long)n_local);
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    free_db(ctx);
+    ctx->n_total = n_total;
+    ctx->shard = (uint32_t)shard;
+    ctx->num_shards = (uint32_t)num_shards;
+    std::vector<uint16_t> len(ltiles * kTileSeqs, 0);
+    std::vector<uint64_t> off(ltiles * kTileSeqs + 1, 0);
+    uint64_t acc = 0;
+    for (uint64_t i = 0; i < len.size(); ++i) {
+        off[i] = acc;
+        if (i < n_local) { len[i] = local_lengths[i]; acc += local_lengths[i]; }    // only the last tile can be partial
+    }
+    off[len.size()] = acc;
+    if (acc != n_local_residues) return fail(ctx, SWG_ERR_ARG, "lengths sum to %llu residues, caller said %llu",
+                                             (unsigned long long)acc, (unsigned long long)n_local_residues);
+    ctx->local_seqs = n_local;
+    ctx->local_residues = acc;
+    return upload_and_build(ctx, len, off, local_residues, nullptr);
+}
+
+int swg_gpu_load_db_interleaved(swg_ctx *ctx, const signed char *vect_db, const uint16_t *vect_lengths, uint64_t vect_count,
+                                const uint64_t *vect_disp, int vector_length, uint64_t n_sequences, int shard, int num_shards)
+{
+    if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
+    if (vector_length != 16 && vector_length != 32) return fail(ctx, SWG_ERR_ARG, "vector_length must be 16 or 32");
+    if (n_sequences > vect_count * (uint64_t)vector_length) return fail(ctx, SWG_ERR_ARG, "more sequences than lanes");
+    if (n_sequences && (!vect_db || !vect_lengths || !vect_disp)) return fail(ctx, SWG_ERR_ARG, "NULL database arrays");
+    // Undo the reference's lane interleave (sequences.c:704-723): lane k of group g holds sequence
+    // g*vector_length + k; its residues are vect_db[disp[g] + j*vector_length + k], padded with code 24.
+    std::vector<uint16_t> lengths(n_sequences);
+    std::vector<uint64_t> start(n_sequences + 1, 0);
+    for (uint64_t s = 0; s < n_sequences; ++s) {
+        const uint64_t g = s / vector_length, k = s % vector_length;
+        const signed char *col = vect_db + vect_disp[g] + k;
+        uint32_t l = vect_lengths[g];
+        while (l > 0 && col[(uint64_t)(l - 1) * vector_length] >= kPadCode) --l;
+        lengths[s] = (uint16_t)l;
+        start[s + 1] = start[s] + l;
+    }
+    std::vector<signed char> flat(std::max<uint64_t>(start[n_sequences], 1));
+    for (uint64_t s = 0; s < n_sequences; ++s) {
+        const uint64_t g = s / vector_length, k = s % vector_length;
+        const signed char *col = vect_db + vect_disp[g] + k;
+        signed char *dst = flat.data() + start[s];
+        for (uint32_t j = 0; j < lengths[s]; ++j) dst[j] = col[(uint64_t)j * vector_length];
+    }
+    return swg_gpu_load_db(ctx, lengths.data(), flat.data(), n_sequences, start[n_sequences], shard, num_shards);
+}
+
+uint64_t swg_gpu_db_local_sequences(const swg_ctx *ctx) { return ctx && ctx->db_ready ? ctx->local_seqs : 0; }
+uint64_t swg_gpu_db_local_residues(const swg_ctx *ctx) { return ctx && ctx->db_ready ? ctx->local_residues : 0; }
+
+// ---- queries -----------------------------------------------------------------------------------
+int swg_gpu_set_queries(swg_ctx *ctx, const signed char *queries, const uint16_t *q_lengths, const uint32_t *q_disp,
+                        uint64_t q_count, const signed char *submat, int open_gap, int extend_gap)
+{
+    if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
+    if (q_count && (!queries || !q_lengths || !q_disp)) return fail(ctx, SWG_ERR_ARG, "NULL query arrays");
+    if (!submat) return fail(ctx, SWG_ERR_ARG, "NULL substitution matrix");
+    if (open_gap < 0 || extend_gap < 0 || open_gap + extend_gap > 4096)
+        return fail(ctx, SWG_ERR_ARG, "gap penalties %d/%d out of range", open_gap, extend_gap);
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->q_count = q_count;
+    ctx->q_len.assign(q_lengths, q_lengths + q_count);
+    ctx->q_off.assign(q_count + 1, 0);
+    for (uint64_t i = 0; i < q_count; ++i) ctx->q_off[i + 1] = ctx->q_off[i] + q_lengths[i];
+    const uint64_t total = ctx->q_off[q_count];
+    SWG_CUDA(ctx, ctx->d_queries.reserve(std::max<uint64_t>(total, 1)));
+    SWG_CUDA(ctx, ctx->d_submat.reserve(768));
+    // queries are packed back to back on the device (the caller's q_disp may leave gaps)
+    for (uint64_t i = 0; i < q_count; ++i)
+        if (q_lengths[i])
+            SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_queries.as<char>() + ctx->q_off[i], queries + q_disp[i], q_lengths[i],
+                                          cudaMemcpyHostToDevice, ctx->stream));
+    SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_submat.p, submat, 768, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->open_gap = open_gap;
+    ctx->extend_gap = extend_gap;
+    ctx->queries_ready = true;
+    ctx->run_done = false;
+    ctx->stats.h2d_bytes = total + 768;
+    return SWG_OK;
+}
+
+int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
+{
+    (void)keep_scores;
+    if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
+    if (!ctx->db_ready) return fail(ctx, SWG_ERR_STATE, "no database loaded");
+    if (!ctx->queries_ready) return fail(ctx, SWG_ERR_STATE, "no queries set");
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nq = ctx->q_count;
+    const uint64_t n_pad = (uint64_t)ctx->ntiles * kTileSeqs;
+    ctx->run_top_stride = top;
+    if (top > ctx->n_total) top = ctx->n_total;      // like the reference (swimm.c:51); the rest of a row stays 0
+    ctx->run_top = top;
+    ctx->stats.launches = 0;
+    ctx->stats.cells = 0;
+    ctx->stats.padded_cells = 0;
+    ctx->stats.rescored = 0;
+
+    const int grid = ctx->sm_count;
+    const size_t warps = (size_t)grid * (kBlockThreads / 32);
+    std::vector<Config> main_cfgs(nq), wide_cfgs(nq);
+    uint32_t max_passes = 1;
+    for (uint64_t q = 0; q < nq; ++q) {
+        main_cfgs[q] = choose_config(ctx->q_len[q], ctx->avg_cols, ctx->force_group, ctx->force_rows);
+        wide_cfgs[q] = wide_config(ctx->q_len[q]);
+        max_passes = std::max(max_passes, std::max(main_cfgs[q].passes, wide_cfgs[q].passes));
+    }
+    SWG_CUDA(ctx, ctx->d_scores.reserve(std::max<uint64_t>(nq * n_pad, 1) * sizeof(int32_t)));
+    SWG_CUDA(ctx, ctx->d_profile.reserve((size_t)max_passes * kPassBytes));
+    SWG_CUDA(ctx, ctx->d_profile32.reserve((size_t)max_passes * kPassBytes));
+    SWG_CUDA(ctx, ctx->d_boundary.reserve(warps * ctx->maxcols * sizeof(uint2)));
+    SWG_CUDA(ctx, ctx->d_counters.reserve(std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t)));
+    SWG_CUDA(ctx, ctx->d_resc_list.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
+    const TopkPlan tp = topk_plan(n_pad, top, nq);
+    SWG_CUDA(ctx, ctx->d_topk_scratch.reserve(tp.scratch_keys * sizeof(uint64_t)));
+    SWG_CUDA(ctx, ctx->d_top_out.reserve(std::max<uint64_t>(nq * top, 1) * sizeof(uint64_t)));
+
+    SWG_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+    SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t), ctx->stream));
+
+    WfParams p;
+    memset(&p, 0, sizeof(p));
+    p.db = ctx->d_db.as<uint4>();
+    p.tile_off = ctx->d_tile_off.as<uint64_t>();
+    p.tile_cols = ctx->d_tile_cols.as<uint32_t>();
+    p.ntiles = ctx->ntiles;
+    p.n_total = ctx->n_total;
+    p.shard = ctx->shard;
+    p.num_shards = ctx->num_shards;
+    p.boundary = ctx->d_boundary.as<uint2>();
+    p.maxcols = ctx->maxcols;
+    p.resc_list = ctx->d_resc_list.as<uint32_t>();
+    p.gap_open_extend = ctx->open_gap + ctx->extend_gap;
+    p.gap_extend = ctx->extend_gap;
+
+    uint64_t padded = 0;
+    for (uint64_t q = 0; q < nq && ctx->ntiles; ++q) {
+        const uint32_t m = ctx->q_len[q];
+        const Config main_cfg = main_cfgs[q];
+        const Config wide_cfg = wide_cfgs[q];
+        uint32_t *cnt = ctx->d_counters.as<uint32_t>() + q * 4;
+        const int8_t *d_q = ctx->d_queries.as<int8_t>() + ctx->q_off[q];
+        p.scores = ctx->d_scores.as<int32_t>() + q * n_pad;
+        p.resc_count = cnt + 3;
+
+        cudaError_t e = launch_build_profile(d_q, m, ctx->d_submat.as<int8_t>(), wide_cfg.G, wide_cfg.K, wide_cfg.passes,
+                                             ctx->d_profile32.as<uint8_t>(), ctx->stream);
+        ctx->stats.launches += 1;
+        const bool same = main_cfg.G == wide_cfg.G && main_cfg.K == wide_cfg.K && main_cfg.passes == wide_cfg.passes &&
+                          main_cfg.global_profile == wide_cfg.global_profile;
+        if (e == cudaSuccess && !same) {
+            e = launch_build_profile(d_q, m, ctx->d_submat.as<int8_t>(), main_cfg.G, main_cfg.K, main_cfg.passes,
+                                     ctx->d_profile.as<uint8_t>(), ctx->stream);
+            ctx->stats.launches += 1;
+        }
+        // long tiles first (they are the critical path), on the 32-thread shape
+        uint32_t main_tiles = ctx->ntiles;
+        if (e == cudaSuccess && !same && ctx->first_long_tile < ctx->ntiles) {
+            main_tiles = ctx->first_long_tile;
+            p.profile = ctx->d_profile32.as<uint8_t>();
+            p.passes = wide_cfg.passes;
+            p.tile_first = ctx->first_long_tile;
+            p.tile_count = ctx->ntiles - ctx->first_long_tile;
+            p.task_counter = cnt + 0;
+            e = launch_wavefront(false, wide_cfg, grid, ctx->stream, p);
+            ctx->stats.launches += 1;
+            for (uint32_t t = p.tile_first; t < ctx->ntiles; ++t)
+                padded += (uint64_t)wide_cfg.passes * wide_cfg.G * wide_cfg.K * (ctx->h_tile_cols[t] + wide_cfg.G - 1) * kTileSeqs;
+        }
+        if (e == cudaSuccess && main_tiles) {
+            p.profile = same ? ctx->d_profile32.as<uint8_t>() : ctx->d_profile.as<uint8_t>();
+            p.passes = main_cfg.passes;
+            p.tile_first = 0;
+            p.tile_count = main_tiles;
+            p.task_counter = cnt + 1;
+            e = launch_wavefront(false, main_cfg, grid, ctx->stream, p);
+            ctx->stats.launches += 1;
+        }
+        if (e == cudaSuccess) {
+            p.profile = ctx->d_profile32.as<uint8_t>();
+            p.passes = wide_cfg.passes;
+            p.tile_first = 0;
+            p.tile_count = ctx->ntiles;
+            p.task_counter = cnt + 2;
+            e = launch_wavefront(true, wide_cfg, grid, ctx->stream, p);
+            ctx->stats.launches += 1;
+        }
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "search kernel launch");
+        ctx->stats.cells += (uint64_t)m * ctx->local_residues;
+        padded += (uint64_t)main_cfg.passes * main_cfg.G * main_cfg.K *
+                  (uint64_t)((ctx->avg_cols + main_cfg.G - 1) * main_tiles) * kTileSeqs;
+    }
+    ctx->stats.padded_cells = padded;
+    SWG_CUDA(ctx, cudaEventRecord(ctx->ev_search_end, ctx->stream));
+    if (ctx->ntiles && top) {
+        cudaError_t e = launch_topk(tp, ctx->d_scores.as<int32_t>(), nq, ctx->n_total, ctx->shard, ctx->num_shards,
+                                    ctx->d_topk_scratch.as<uint64_t>(), ctx->d_top_out.as<uint64_t>(), ctx->stream,
+                                    &ctx->stats.launches);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "top-r launch");
+    } else if (nq * top) {
+        SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_top_out.p, 0, nq * top * sizeof(uint64_t), ctx->stream));
+    }
+    SWG_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
+    ctx->run_done = true;
+    return SWG_OK;
+}
+
+int swg_gpu_sync(swg_ctx *ctx)
+{
+    if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SWG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->run_done) {
+        float ms_all = 0.f, ms_search = 0.f;
+        SWG_CUDA(ctx, cudaEventElapsedTime(&ms_all, ctx->ev_begin, ctx->ev_end));
+        SWG_CUDA(ctx, cudaEventElapsedTime(&ms_search, ctx->ev_begin, ctx->ev_search_end));
+        ctx->stats.device_seconds = ms_all * 1e-3;
+        ctx->stats.search_seconds = ms_search * 1e-3;
+        ctx->stats.topr_seconds = (ms_all - ms_search) * 1e-3;
+    }
+    return SWG_OK;
+}
+
+int swg_gpu_fetch(swg_ctx *ctx, int32_t *scores, uint64_t *top_keys)
+{
+    if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
+    if (!ctx->run_done) return fail(ctx, SWG_ERR_STATE, "fetch without a run");
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nq = ctx->q_count, n_pad = (uint64_t)ctx->ntiles * kTileSeqs;
+    uint64_t d2h = 0;
+    if (top_keys && nq * ctx->run_top_stride) {
+        // rows of the caller's array are `top` keys apart; the device holds min(top, n) keys per query
+        if (ctx->run_top != ctx->run_top_stride) memset(top_keys, 0, nq * ctx->run_top_stride * sizeof(uint64_t));
+        if (ctx->run_top)
+            SWG_CUDA(ctx, cudaMemcpy2DAsync(top_keys, ctx->run_top_stride * sizeof(uint64_t), ctx->d_top_out.p,
+                                            ctx->run_top * sizeof(uint64_t), ctx->run_top * sizeof(uint64_t), nq,
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+        d2h += nq * ctx->run_top * sizeof(uint64_t);
+    }
+    std::vector<int32_t> local;
+    if (scores && nq * n_pad) {
+        local.resize(nq * n_pad);
+        SWG_CUDA(ctx, cudaMemcpyAsync(local.data(), ctx->d_scores.p, nq * n_pad * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        d2h += nq * n_pad * sizeof(int32_t);
+    }
+    uint32_t resc = 0;
+    std::vector<uint32_t> cnt(std::max<uint64_t>(nq, 1) * 4, 0);
+    if (nq)
+        SWG_CUDA(ctx, cudaMemcpyAsync(cnt.data(), ctx->d_counters.p, nq * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    const int st = swg_gpu_sync(ctx);
+    if (st != SWG_OK) return st;
+    for (uint64_t q = 0; q < nq; ++q) resc += cnt[q * 4 + 3];
+    ctx->stats.rescored = resc;
+    ctx->stats.d2h_bytes = d2h;
+    if (scores) {
+        // local (tile-sharded) order -> positions in the whole length-sorted database
+        for (uint64_t q = 0; q < nq; ++q)
+            for (uint64_t ls = 0; ls < n_pad; ++ls) {
+                const uint64_t g = ((ls / kTileSeqs) * ctx->num_shards + ctx->shard) * kTileSeqs + (ls % kTileSeqs);
+                if (g < ctx->n_total) scores[q * ctx->n_total + g] = local[q * n_pad + ls];
+            }
+    }
+    return SWG_OK;
+}
+
+int swg_gpu_search(swg_ctx *ctx, const signed char *queries, const uint16_t *q_lengths, const uint32_t *q_disp,
+                   uint64_t q_count, const signed char *submat, int open_gap, int extend_gap, uint64_t top, int32_t *scores,
+                   uint64_t *top_keys, double *work_seconds)
+{
+    int st = swg_gpu_set_queries(ctx, queries, q_lengths, q_disp, q_count, submat, open_gap, extend_gap);
+    if (st == SWG_OK) st = swg_gpu_run(ctx, top_keys ? top : 0, scores != nullptr);
+    if (st == SWG_OK) st = swg_gpu_fetch(ctx, scores, top_keys);
+    if (st == SWG_OK && work_seconds) *work_seconds = ctx->stats.search_seconds;
+    return st;
+}
+
+int swg_gpu_get_stats(swg_ctx *ctx, swg_stats *out)
+{
+    if (!ctx || !out) return fail(ctx, SWG_ERR_ARG, "NULL argument");
+    *out = ctx->stats;
+    return SWG_OK;
+}
+
+int swg_gpu_pipebench(swg_ctx *ctx, int max_probes, double *ginstr_per_s, double *sm_mhz, const char **names, int *n_probes,
+                      int *sm_count)
+{
+    if (!ctx || !ginstr_per_s || !sm_mhz || !n_probes) return fail(ctx, SWG_ERR_ARG, "NULL argument");
+    const int n = pipebench_probe_count();
+    if (max_probes < n) return fail(ctx, SWG_ERR_ARG, "need room for %d probes", n);
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SWG_CUDA(ctx, run_pipebench_all(ginstr_per_s, sm_mhz, sm_count, ctx->stream));
+    if (names)
+        for (int p = 0; p < n; ++p) names[p] = pipebench_probe_name(p);
+    *n_probes = n;
+    return SWG_OK;
+}
+
+// ---- the reference's kernel signature (CPUsearch.h:37-39) ------------------------------------------
+int swimm_gpu_search_avx2_compat(char *query_sequences, unsigned short int *query_sequences_lengths,
+                                 unsigned long int query_sequences_count, unsigned int *query_disp, char *vect_sequences_db,
+                                 unsigned short int *vect_sequences_db_lengths, unsigned short int *vect_sequences_db_blocks,
+                                 unsigned long int vect_sequences_db_count, unsigned long int *vect_sequences_db_disp,
+                                 char *submat, int open_gap, int extend_gap, int n_threads, int cpu_block_size, int *scores,
+                                 double *workTime)
+{
+    (void)vect_sequences_db_blocks;
+    (void)cpu_block_size;
+    (void)n_threads;
+    const int vl = 32;
+    if (!scores) return fail(nullptr, SWG_ERR_ARG, "scores is NULL");
+    swg_ctx *ctx = nullptr;
+    int st = swg_gpu_create(0, &ctx);
+    if (st != SWG_OK) return st;
+    const uint64_t lanes = (uint64_t)vect_sequences_db_count * vl;
+    std::vector<uint64_t> disp(vect_sequences_db_count + 1);
+    for (uint64_t g = 0; g <= vect_sequences_db_count; ++g) disp[g] = vect_sequences_db_disp[g];
+    // every lane is searched; lanes that are pure padding have length 0 and score 0, as in the reference
+    st = swg_gpu_load_db_interleaved(ctx, (const signed char *)vect_sequences_db, vect_sequences_db_lengths,
+                                     vect_sequences_db_count, disp.data(), vl, lanes, 0, 1);
+    if (st == SWG_OK)
+        st = swg_gpu_search(ctx, (const signed char *)query_sequences, query_sequences_lengths, query_disp,
+                            query_sequences_count, (const signed char *)submat, open_gap, extend_gap, 0, scores, nullptr,
+                            workTime);
+    if (st != SWG_OK) snprintf(g_last_error, sizeof(g_last_error), "%s", ctx->err);
+    swg_gpu_destroy(ctx);
+    return st;
+}
+
+}  // extern "C"

@@ -23,7 +23,7 @@
 
 namespace swg {
 
-template <class L, int G, int K>
+template <class L, int G, int K, bool GP>
 __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfParams p)
 {
     typedef typename L::reg reg;
@@ -34,10 +34,13 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
     constexpr int TPT = (L::kSeqs == 2) ? (kTilePairs / GPW) : 1;   // warp tasks per tile
     constexpr int KCH = (K + 15) / 16;                // 16-row profile chunks per thread
 
-    extern __shared__ __align__(16) uint8_t prof[];
-    {
+    // GP ("global profile"): queries with more passes than fit in shared memory read the profile through L1
+    extern __shared__ __align__(16) uint8_t prof_smem[];
+    const uint8_t *prof = GP ? p.profile : prof_smem;
+    if (L::kSeqs == 1 && *p.resc_count == 0) return;      // nothing left the 16-bit range
+    if (!GP) {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.profile);
-        uint4 *dst = reinterpret_cast<uint4 *>(prof);
+        uint4 *dst = reinterpret_cast<uint4 *>(prof_smem);
         const int n16 = (int)(p.passes * (kPassBytes / 16));
         for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
     }
@@ -199,28 +202,29 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
     }
 }
 
-// host-side launcher of one (lane policy, group size) family; defined in wavefront_inst_*.cu
-typedef cudaError_t (*wf_launch_fn)(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
-
+// host-side launchers; one translation unit per (lane policy, group size) family (wavefront_inst_*.cu)
 cudaError_t launch_wf_l16_g4(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
 cudaError_t launch_wf_l16_g8(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
 cudaError_t launch_wf_l16_g16(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
 cudaError_t launch_wf_l16_g32(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
 cudaError_t launch_wf_l32_g32(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
+// the two "profile in global memory" variants (G = 32, K = 32) for queries of more than kMaxSmemPasses passes
+cudaError_t launch_wf_l16_gp(int grid, cudaStream_t stream, const WfParams &p);
+cudaError_t launch_wf_l32_gp(int grid, cudaStream_t stream, const WfParams &p);
 
-template <class L, int G, int K>
+template <class L, int G, int K, bool GP>
 cudaError_t launch_one(int grid, size_t smem, cudaStream_t stream, const WfParams &p)
 {
     static size_t configured[64] = {0};            // per device: the attribute lives in the device's context
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(wavefront_kernel<L, G, K>,
+        cudaError_t e = cudaFuncSetAttribute(wavefront_kernel<L, G, K, GP>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = smem;
     }
-    wavefront_kernel<L, G, K><<<grid, kBlockThreads, smem, stream>>>(p);
+    wavefront_kernel<L, G, K, GP><<<grid, kBlockThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -179,6 +179,34 @@ def read_preprocessed(prefix: str) -> tuple[np.ndarray, np.ndarray, int]:
     return lengths, codes, mt
 
 
+def interleave_reference(lengths: np.ndarray, codes: np.ndarray, vector_length: int = 32, block: int = 60):
+    """The lane-interleaved arrays the reference driver hands to its kernels (what
+    assemble_single_chunk_db builds, reference sequences.c:618-734): groups of `vector_length`
+    consecutive sorted sequences, group length = longest member rounded up to a multiple of 5,
+    residue j of lane k at disp[g] + j*vector_length + k, padding code 24.
+    Returns (vect_db int8, vect_lengths u16, vect_blocks u16, vect_disp u64[groups+1])."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    n = len(lengths)
+    groups = (n + vector_length - 1) // vector_length
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lengths, out=off[1:])
+    vlen = np.zeros(groups, dtype=np.int64)
+    for g in range(groups):
+        last = min(n, (g + 1) * vector_length) - 1
+        vlen[g] = (lengths[last] + 4) // 5 * 5
+    disp = np.zeros(groups + 1, dtype=np.uint64)
+    np.cumsum((vlen * vector_length).astype(np.uint64), out=disp[1:])
+    vdb = np.full(int(disp[-1]), 24, dtype=np.int8)
+    for g in range(groups):
+        view = vdb[int(disp[g]):int(disp[g + 1])].reshape(int(vlen[g]), vector_length)
+        for k in range(vector_length):
+            s = g * vector_length + k
+            if s < n:
+                view[:lengths[s], k] = codes[off[s]:off[s + 1]]
+    blocks = ((vlen + block - 1) // block).astype(np.uint16)
+    return vdb, vlen.astype(np.uint16), blocks, disp
+
+
 def workload(name: str, scale: float = 1.0):
     """Named BASELINE.json configurations -> (db SeqSet, queries SeqSet).  `scale` shrinks the
     sequence count (tests use small scales; bench uses 1.0)."""

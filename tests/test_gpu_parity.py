@@ -1,0 +1,226 @@
+"""Parity of the CUDA path (through the C ABI, include/swimm_gpu.h) with the oracle and with the golden
+vectors of the unmodified reference.  Integer work: the bar is bit-exact scores and identical hit order."""
+import numpy as np
+import pytest
+
+from swimm_b200 import host, synth
+from tests.helpers import GOLDEN_CASES, GoldenCase
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "gpu-marked test collected without a CUDA device"
+    from swimm_b200 import gpu as g
+    s = g.GpuSearch(0)
+    yield s
+    s.close()
+
+
+def _keys_to_order(keys):
+    from swimm_b200.gpu import split_key
+    return split_key(keys)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_scores_and_order(gpu, name):
+    case = GoldenCase(name)
+    gpu.load_db(case.db_len, case.db_codes)
+    for matrix, go, ge, exp_scores, order in case.runs():
+        scores, keys = gpu.search(case.q_codes, case.q_len, case.q_off[:-1], host.submat(matrix), go, ge, case.db.n,
+                                  want_scores=True)
+        assert np.array_equal(scores, exp_scores), (name, matrix, go, ge, np.argwhere(scores != exp_scores)[:5])
+        ks, ki = _keys_to_order(keys)
+        assert np.array_equal(ki, order), (name, matrix, "hit order")
+        assert np.array_equal(ks, np.take_along_axis(exp_scores.astype(np.int64), order, axis=1))
+    st = gpu.stats()
+    if name == "overflow":
+        assert st["rescored"] > 0          # the 32-bit kernel must have run
+
+
+@pytest.mark.parametrize("top", [1, 10, 100])
+def test_golden_top_r_small(gpu, top):
+    case = GoldenCase("basic")
+    gpu.load_db(case.db_len, case.db_codes)
+    matrix, go, ge, exp_scores, order = next(case.runs())
+    _, keys = gpu.search(case.q_codes, case.q_len, case.q_off[:-1], host.submat(matrix), go, ge, top)
+    ks, ki = _keys_to_order(keys)
+    assert np.array_equal(ki, order[:, :top])
+
+
+def _random_case(seed, n, qlens, mu=4.5, sigma=0.7, hi=1500, plant=0.05):
+    rng = np.random.default_rng(seed)
+    q = synth.make_queries(rng, qlens)
+    db = synth.make_seqset(rng, synth.lognormal_lengths(rng, n, mu, sigma, 1, hi))
+    synth.plant(rng, db, q, fraction=plant, frag_range=(5, 200), rate=0.1)
+    perm, dlen, dcodes = synth.length_sorted(db)
+    _, qlen, qcodes = synth.length_sorted(q)
+    doff = np.zeros(db.n + 1, np.uint64)
+    np.cumsum(dlen.astype(np.uint64), out=doff[1:])
+    qoff = np.zeros(q.n + 1, np.uint32)
+    np.cumsum(qlen.astype(np.uint32), out=qoff[1:])
+    return qcodes, qlen, qoff, dcodes, dlen, doff
+
+
+@pytest.mark.parametrize("qlens", [[1, 2, 3], [4, 17, 31, 32, 33], [63, 64, 65, 127, 128, 129], [144, 255, 257],
+                                   [511, 513, 700], [1023, 1025], [1500, 2100]])
+def test_random_vs_oracle_query_shapes(gpu, oracle, qlens):
+    """Every (group size, rows per thread, passes) shape the planner can choose."""
+    qc, ql, qo, dc, dl, do = _random_case(100 + len(qlens) + qlens[0], 700, qlens)
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    gpu.load_db(dl, dc)
+    got, keys = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 25, want_scores=True)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:8]
+    for qi in range(len(ql)):
+        ts, ti = oracle.top(want[qi], 25)
+        ks, ki = _keys_to_order(keys[qi])
+        assert np.array_equal(ki, ti.astype(np.int64)) and np.array_equal(ks, ts)
+
+
+@pytest.mark.parametrize("G", [4, 8, 16, 32])
+@pytest.mark.parametrize("K", [1, 2, 7, 16, 17, 32])
+def test_forced_shapes_vs_oracle(gpu, oracle, G, K):
+    m = G * K - (1 if K > 1 else 0)
+    qc, ql, qo, dc, dl, do = _random_case(7 * G + K, 300, [max(1, m // 2), m], hi=600)
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum50"), 11, 1)
+    gpu.load_db(dl, dc)
+    gpu.set_option("force_group", G)
+    gpu.set_option("force_rows", K)
+    try:
+        got, _ = gpu.search(qc, ql, qo[:-1], host.submat("blosum50"), 11, 1, 0, want_scores=True)
+    finally:
+        gpu.set_option("force_group", 0)
+        gpu.set_option("force_rows", 0)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:8]
+
+
+def test_matrix_and_penalty_sweep(gpu, oracle):
+    qc, ql, qo, dc, dl, do = _random_case(31, 400, [30, 90, 150, 222])
+    gpu.load_db(dl, dc)
+    for mat in ["blosum45", "blosum80", "pam30", "pam250"]:
+        for go in [5, 8, 10, 12]:
+            for ge in [1, 2, 3]:
+                want = oracle.search(qc, qo, dc, do, host.submat(mat), go, ge)
+                got, _ = gpu.search(qc, ql, qo[:-1], host.submat(mat), go, ge, 0, want_scores=True)
+                assert np.array_equal(got, want), (mat, go, ge)
+
+
+def test_long_sequences_and_32bit_rescore(gpu, oracle):
+    """cfg4 in miniature: database sequences above the long-sequence threshold, planted near-copies of a long
+    query (score > 32767 -> 32-bit kernel) and partial homologs."""
+    rng = np.random.default_rng(77)
+    q = synth.make_queries(rng, [300, 3300])
+    lens = np.concatenate([rng.integers(3001, 9000, 40), rng.integers(50, 400, 60), [20000, 40000]])
+    db = synth.make_seqset(rng, lens)
+    big = q.seq(1)
+    for t, rate in [(3, 0.0), (10, 0.02), (41, 0.3)]:
+        s = db.offsets[t]
+        L = min(len(big), db.offsets[t + 1] - s)
+        db.residues[s:s + L] = synth.mutate(rng, big[:L], rate)
+    perm, dl, dc = synth.length_sorted(db)
+    _, ql, qc = synth.length_sorted(q)
+    do = np.zeros(db.n + 1, np.uint64)
+    np.cumsum(dl.astype(np.uint64), out=do[1:])
+    qo = np.zeros(q.n + 1, np.uint32)
+    np.cumsum(ql.astype(np.uint32), out=qo[1:])
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    assert want.max() > 32767
+    gpu.load_db(dl, dc)
+    got, keys = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 10, want_scores=True)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:8]
+    assert gpu.stats()["rescored"] > 0
+    for qi in range(2):
+        ts, ti = oracle.top(want[qi], 10)
+        ks, ki = _keys_to_order(keys[qi])
+        assert np.array_equal(ki, ti.astype(np.int64)) and np.array_equal(ks, ts)
+
+
+def test_very_long_query_global_profile(gpu, oracle):
+    """More passes than fit in shared memory: the kernel variant that reads the profile through L1."""
+    qc, ql, qo, dc, dl, do = _random_case(5, 64, [9000], hi=300)
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    gpu.load_db(dl, dc)
+    got, _ = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 0, want_scores=True)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_search_merges_to_unsharded(gpu, oracle, shards):
+    """Multi-GPU path on one device: every shard searched in turn, hit lists merged on the host."""
+    from swimm_b200.gpu import merge_top_keys
+    qc, ql, qo, dc, dl, do = _random_case(61, 1000, [50, 144])
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    top = 20
+    parts, all_scores = [], np.zeros_like(want)
+    residues = 0
+    for s in range(shards):
+        gpu.load_db(dl, dc, shard=s, num_shards=shards)
+        residues += gpu.local_residues
+        sc, keys = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, top, want_scores=True)
+        parts.append(keys)
+        all_scores |= sc            # each shard writes only its own sequences, the rest stay 0
+    assert residues == int(dl.astype(np.int64).sum())
+    assert np.array_equal(all_scores, want)
+    merged = merge_top_keys(parts, top)
+    for qi in range(len(ql)):
+        ts, ti = oracle.top(want[qi], top)
+        ks, ki = _keys_to_order(merged[qi])
+        assert np.array_equal(ki, ti.astype(np.int64)) and np.array_equal(ks, ts)
+        one = host.merge_top_keys(np.stack([p[qi] for p in parts]), top)
+        assert np.array_equal(one, merged[qi])
+
+
+def test_reference_signature_entry_point(oracle):
+    """swimm_gpu_search_avx2_compat takes exactly what swimm.c:74-76 hands to cpu_search_avx2_sp."""
+    from swimm_b200 import gpu as g
+    qc, ql, qo, dc, dl, do = _random_case(88, 150, [21, 144])
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    # the reference's query padding (odd -> even with the dummy residue, sequences.c:367-387)
+    m = (ql + (ql & 1)).astype(np.uint16)
+    qdisp = np.zeros(len(ql) + 1, np.uint32)
+    np.cumsum(m, out=qdisp[1:])
+    qpad = np.full(int(qdisp[-1]), 23, np.int8)
+    for i in range(len(ql)):
+        qpad[qdisp[i]:qdisp[i] + ql[i]] = qc[qo[i]:qo[i + 1]]
+    vdb, vlen, vblocks, vdisp = synth.interleave_reference(dl, dc, 32, 60)
+    scores, work = g.compat_search_avx2(qpad, m, qdisp, vdb, vlen, vblocks, vdisp, host.submat("blosum62"), 10, 2)
+    n = len(dl)
+    assert np.array_equal(scores[:, :n], want)
+    assert (scores[:, n:] == 0).all()
+    assert work > 0
+
+
+def test_round_trip_properties_at_scale(gpu):
+    """Size-independent checks on a database too large for the oracle to finish in seconds:
+    self-hit = sum of diagonal scores, top-r idempotent under re-sharding, scores symmetric in (q, d) roles."""
+    rng = np.random.default_rng(3)
+    q = synth.make_queries(rng, [200])
+    db = synth.make_db(9, 60_000, queries=q)
+    # plant the query itself: its score against the copy is the sum of the matrix diagonal over its residues
+    t = int(np.argmax(db.lengths >= 400))
+    db.residues[db.offsets[t] + 7: db.offsets[t] + 207] = q.seq(0)
+    perm, dl, dc = synth.length_sorted(db)
+    _, ql, qc = synth.length_sorted(q)
+    b62 = host.submat("blosum62")
+    gpu.load_db(dl, dc)
+    scores, keys = gpu.search(qc, ql, np.zeros(1, np.uint32), b62, 10, 2, 10, want_scores=True)
+    self_score = int(sum(b62[c, c] for c in qc))
+    pos = int(np.where(perm == t)[0][0])
+    assert scores[0, pos] == self_score
+    from swimm_b200.gpu import split_key, merge_top_keys
+    ks, ki = split_key(keys[0])
+    assert ki[0] == pos and ks[0] == self_score
+    # order property of the keys: strictly descending
+    assert (np.diff(keys[0].astype(np.int64)) < 0).all()
+    # the same top-10 from 4 shards
+    parts = []
+    for s in range(4):
+        gpu.load_db(dl, dc, shard=s, num_shards=4)
+        _, k = gpu.search(qc, ql, np.zeros(1, np.uint32), b62, 10, 2, 10)
+        parts.append(k)
+    assert np.array_equal(merge_top_keys(parts, 10), keys)
+    # numpy check of the top-10 against the full score vector
+    order = np.lexsort((-np.arange(len(dl)), -scores[0].astype(np.int64)))[:10]
+    assert np.array_equal(ki, order)
