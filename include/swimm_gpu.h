@@ -109,6 +109,10 @@ int swg_gpu_get_stats(swg_ctx *ctx, swg_stats *out);
 int swg_gpu_pipebench(swg_ctx *ctx, int max_probes, double *ginstr_per_s, double *sm_mhz, const char **names,
                       int *n_probes, int *sm_count);
 
+/* diagnostics: copy an internal device buffer to the host.  name in {"db", "tile_off", "tile_cols", "profile",
+ * "profile32", "scores", "counters"}; *bytes receives the buffer's size, at most max_bytes are copied. */
+int swg_gpu_debug_read(swg_ctx *ctx, const char *name, void *out, uint64_t max_bytes, uint64_t *bytes);
+
 /* tuning knobs (all optional): name in {"long_threshold", "force_group", "force_rows", "block_threads"} */
 int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value);
 

@@ -120,7 +120,7 @@ probe_kernel(uint32_t *out, uint32_t iters, const uint32_t *consts, long long *c
                 else if (P == P_IDP4A) v[c] = __dp4a((int)v[c], (int)k1, (int)e[c]);
                 else if (P == P_MIX65 || P == P_MIX55_IMAD) {
                     // one cell pair of the kernel: score pack, H, E, F and (every other cell) the running best
-                    const uint32_t s = __byte_perm(e[c], f[c], 0xc480 + (u & 3) * 0x1111);
+                    const uint32_t s = prmt(e[c], f[c], 0xc480 + (u & 3) * 0x1111);
                     const uint32_t a = __viaddmax_s16x2(d[c], s, e[c]);
                     const uint32_t h = __vimax3_s16x2(a, f[c], k3);
                     uint32_t open;

@@ -778,6 +778,28 @@ int swg_gpu_get_stats(swg_ctx *ctx, swg_stats *out)
     return SWG_OK;
 }
 
+int swg_gpu_debug_read(swg_ctx *ctx, const char *name, void *out, uint64_t max_bytes, uint64_t *bytes)
+{
+    if (!ctx || !name || !bytes) return fail(ctx, SWG_ERR_ARG, "NULL argument");
+    const DeviceBuf *b = nullptr;
+    uint64_t n = 0;
+    if (!strcmp(name, "db")) { b = &ctx->d_db; n = ctx->db_units * sizeof(uint4); }
+    else if (!strcmp(name, "tile_off")) { b = &ctx->d_tile_off; n = ((uint64_t)ctx->ntiles + 1) * sizeof(uint64_t); }
+    else if (!strcmp(name, "tile_cols")) { b = &ctx->d_tile_cols; n = (uint64_t)ctx->ntiles * sizeof(uint32_t); }
+    else if (!strcmp(name, "profile")) { b = &ctx->d_profile; n = b->cap; }
+    else if (!strcmp(name, "profile32")) { b = &ctx->d_profile32; n = b->cap; }
+    else if (!strcmp(name, "scores")) { b = &ctx->d_scores; n = ctx->q_count * ctx->ntiles * kTileSeqs * sizeof(int32_t); }
+    else if (!strcmp(name, "counters")) { b = &ctx->d_counters; n = ctx->q_count * 4 * sizeof(uint32_t); }
+    else return fail(ctx, SWG_ERR_ARG, "unknown buffer '%s'", name);
+    *bytes = n;
+    if (!out || !n) return SWG_OK;
+    if (n > max_bytes) n = max_bytes;
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SWG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SWG_CUDA(ctx, cudaMemcpy(out, b->p, n, cudaMemcpyDeviceToHost));
+    return SWG_OK;
+}
+
 int swg_gpu_pipebench(swg_ctx *ctx, int max_probes, double *ginstr_per_s, double *sm_mhz, const char **names, int *n_probes,
                       int *sm_count)
 {

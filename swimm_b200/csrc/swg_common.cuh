@@ -60,6 +60,15 @@ __device__ __forceinline__ uint64_t global_seq_index(const WfParams &p, uint32_t
     return ((uint64_t)ltile * p.num_shards + p.shard) * kTileSeqs + (local_seq % kTileSeqs);
 }
 
+// PRMT with the full 4-bit selectors: bit 3 of a nibble replicates the sign of the selected byte over the
+// target byte (this is what sign-extends the 8-bit profile entries).  __byte_perm() masks that bit away.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 // ---- lane policies ---------------------------------------------------------------------------------
 // Lane16: two database sequences per thread group in the halves of a 32-bit register (s16x2 DPX).
 // Lane32: one sequence per group, plain int32 DPX -- the exact re-computation of overflowed lanes.
@@ -77,7 +86,7 @@ struct Lane16 {
     static __device__ __forceinline__ reg score(uint32_t w_lo, uint32_t w_hi)
     {
         constexpr uint32_t sel = (uint32_t)B | ((8u | B) << 4) | ((4u + B) << 8) | ((12u + B) << 12);
-        return __byte_perm(w_lo, w_hi, sel);
+        return prmt(w_lo, w_hi, sel);
     }
 };
 
@@ -94,7 +103,7 @@ struct Lane32 {
     static __device__ __forceinline__ reg score(uint32_t w_lo, uint32_t)
     {
         constexpr uint32_t sel = (uint32_t)B | ((8u | B) << 4) | ((8u | B) << 8) | ((8u | B) << 12);
-        return (int32_t)__byte_perm(w_lo, 0u, sel);
+        return (int32_t)prmt(w_lo, 0u, sel);
     }
 };
 

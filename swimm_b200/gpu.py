@@ -18,7 +18,7 @@ ABI_SYMBOLS = [
     "swg_gpu_device_count", "swg_gpu_create", "swg_gpu_destroy", "swg_gpu_last_error", "swg_gpu_load_db",
     "swg_gpu_load_db_shard", "swg_gpu_load_db_interleaved", "swg_gpu_db_local_sequences", "swg_gpu_db_local_residues", "swg_gpu_search",
     "swg_gpu_set_queries", "swg_gpu_run", "swg_gpu_fetch", "swg_gpu_sync", "swg_gpu_get_stats", "swg_gpu_pipebench",
-    "swg_gpu_set_option", "swimm_gpu_search_avx2_compat",
+    "swg_gpu_set_option", "swg_gpu_debug_read", "swimm_gpu_search_avx2_compat",
 ]
 
 
@@ -68,6 +68,7 @@ def load_library() -> C.CDLL:
     L.swg_gpu_sync.argtypes = [vp]
     L.swg_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.swg_gpu_pipebench.argtypes = [vp, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
+    L.swg_gpu_debug_read.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     L.swg_gpu_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.swimm_gpu_search_avx2_compat.argtypes = [vp, vp, C.c_ulong, vp, vp, vp, vp, C.c_ulong, vp, vp, i32, i32, i32, i32,
                                                vp, C.POINTER(C.c_double)]
@@ -199,6 +200,14 @@ class GpuSearch:
         s = Stats()
         self._check(self.L.swg_gpu_get_stats(self.ctx, C.byref(s)), "get_stats")
         return s.as_dict()
+
+    def debug_read(self, name: str, dtype=np.uint8) -> np.ndarray:
+        n = C.c_uint64(0)
+        self._check(self.L.swg_gpu_debug_read(self.ctx, name.encode(), None, 0, C.byref(n)), "debug_read")
+        buf = np.zeros(n.value, dtype=np.uint8)
+        if n.value:
+            self._check(self.L.swg_gpu_debug_read(self.ctx, name.encode(), buf.ctypes.data, n.value, C.byref(n)), "debug_read")
+        return buf.view(dtype)
 
     def pipebench(self) -> dict:
         n, sms = C.c_int(0), C.c_int(0)

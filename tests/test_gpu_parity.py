@@ -111,11 +111,11 @@ def test_long_sequences_and_32bit_rescore(gpu, oracle):
     """cfg4 in miniature: database sequences above the long-sequence threshold, planted near-copies of a long
     query (score > 32767 -> 32-bit kernel) and partial homologs."""
     rng = np.random.default_rng(77)
-    q = synth.make_queries(rng, [300, 3300])
-    lens = np.concatenate([rng.integers(3001, 9000, 40), rng.integers(50, 400, 60), [20000, 40000]])
+    q = synth.make_queries(rng, [300, 7000])
+    lens = np.concatenate([rng.integers(3001, 9000, 40), rng.integers(50, 400, 60), [7500, 8000, 20000, 40000]])
     db = synth.make_seqset(rng, lens)
     big = q.seq(1)
-    for t, rate in [(3, 0.0), (10, 0.02), (41, 0.3)]:
+    for t, rate in [(100, 0.0), (101, 0.02), (3, 0.3), (41, 0.3)]:
         s = db.offsets[t]
         L = min(len(big), db.offsets[t + 1] - s)
         db.residues[s:s + L] = synth.mutate(rng, big[:L], rate)
