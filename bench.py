@@ -296,8 +296,9 @@ def main():
     roof = None
     if not args.no_pipebench:
         pb = s.pipebench()
-        mix = pb["probes"]["mix_6p5_dpx"]
-        # 6.5 integer-pipe instructions per 2 cells (one s16x2 lane pair): peak cells/s = instr/s * 2 / 6.5
+        mix = pb["probes"]["mix_v2_4p5_alu_2_viadd"]
+        # the kernel's own 6.5 integer instructions per 2 cells (one s16x2 lane pair), dependency-free:
+        # peak cells/s = instr/s * 2 / 6.5
         peak_gcups = mix["ginstr_per_s"] * 2.0 / 6.5
         per_gpu = cells_local * args.steps / dev_s / 1e9
         search_gcups = cells_local * args.steps / search_s / 1e9
@@ -308,8 +309,9 @@ def main():
         roof = {"bound": "int_alu", "achieved": search_gcups, "peak": peak_gcups, "unit": "GCUPS",
                 "frac": search_gcups / peak_gcups, "traffic": None,
                 "kernel": "wavefront_kernel<Lane16,G,K> (all 16-bit search launches of a step)",
-                "mix": "6.5 ALU-pipe instr per 2 cells (VIADDMNMX x3, VIMNMX3 x1.5, VIADD.16x2, PRMT), measured %.1f "
-                       "thread-instr/clk/SM at %.0f MHz" % (mix["thread_instr_per_clk_per_sm"], mix["sm_mhz"]),
+                "mix": "6.5 integer instr per 2 cells: 4.5 on the ALU pipe (PRMT, VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + "
+                       "2 VIADD.16x2; measured %.1f thread-instr/clk/SM at %.0f MHz"
+                       % (mix["thread_instr_per_clk_per_sm"], mix["sm_mhz"]),
                 "whole_step_gcups_per_gpu": per_gpu,
                 "hbm": {"bound": "hbm", "achieved": algo_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": algo_gbs / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json"))

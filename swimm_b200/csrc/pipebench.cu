@@ -28,19 +28,21 @@ constexpr int kUnroll = 16;      // cells per chain per loop trip (loop overhead
 enum Probe {
     P_VIADDMNMX = 0, P_VIMNMX, P_VIMNMX_RELU, P_VIMNMX3, P_VIADD16, P_PRMT, P_IMAD, P_IADD3, P_LOP3,
     P_HFMA2, P_HMNMX2, P_IDP4A, P_MIX65, P_MIX55_IMAD, P_PAIR_DPX_IMAD, P_PAIR_DPX_HFMA2, P_PAIR_DPX_PRMT,
-    P_PAIR_DPX_IDP, P_SHFL, P_LDS128, P_PAIR_DPX_SHFL, P_PAIR_DPX_LDS, P_COUNT
+    P_PAIR_DPX_IDP, P_SHFL, P_LDS128, P_PAIR_DPX_SHFL, P_PAIR_DPX_LDS, P_MIX_V2, P_PAIR_DPX_VIADD, P_PAIR_DPX_HMNMX2,
+    P_PAIR_DPX_FFMA, P_PAIR_VIADD_IMAD, P_COUNT
 };
 
 const char *const kProbeName[P_COUNT] = {
     "viaddmnmx_s16x2", "vimnmx_s16x2", "vimnmx3_s16x2_relu", "vimnmx3_s16x2", "viadd_16x2", "prmt", "imad",
     "iadd3_two_fused_adds", "lop3", "hfma2", "hmnmx2", "idp4a", "mix_6p5_dpx", "mix_5p5_dpx_plus_imad", "pair_viaddmnmx_imad",
     "pair_viaddmnmx_hfma2", "pair_viaddmnmx_prmt", "pair_viaddmnmx_idp4a", "shfl_up", "lds128",
-    "pair_viaddmnmx_shfl", "pair_viaddmnmx_lds128"};
+    "pair_viaddmnmx_shfl", "pair_viaddmnmx_lds128", "mix_v2_4p5_alu_2_viadd", "pair_viaddmnmx_viadd16x2",
+    "pair_viaddmnmx_hmnmx2", "pair_viaddmnmx_ffma", "pair_viadd16x2_imad"};
 
 // thread-instructions counted per inner step of one chain
 __host__ __device__ constexpr double probe_instr(int p)
 {
-    return p == P_MIX65 ? 6.5 : p == P_MIX55_IMAD ? 6.5 : p == P_IADD3 ? 0.5 : (p >= P_PAIR_DPX_IMAD && p <= P_PAIR_DPX_IDP) ? 2.0
+    return p == P_MIX65 ? 6.5 : p == P_MIX_V2 ? 6.5 : (p >= P_PAIR_DPX_VIADD && p <= P_PAIR_VIADD_IMAD) ? 2.0 : p == P_MIX55_IMAD ? 6.5 : p == P_IADD3 ? 0.5 : (p >= P_PAIR_DPX_IMAD && p <= P_PAIR_DPX_IDP) ? 2.0
          : (p == P_PAIR_DPX_SHFL || p == P_PAIR_DPX_LDS) ? 2.0 : 1.0;
 }
 
@@ -68,6 +70,12 @@ __device__ __forceinline__ uint32_t lop3_u(uint32_t a, uint32_t b, uint32_t c)
     asm volatile("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+__device__ __forceinline__ uint32_t ffma_u(uint32_t a, uint32_t b, uint32_t c)
+{
+    float d;
+    asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c)));
+    return __float_as_uint(d);
+}
 __device__ __forceinline__ uint32_t hmin2_u(uint32_t a, uint32_t b)
 {
     uint32_t d;
@@ -88,7 +96,7 @@ probe_kernel(uint32_t *out, uint32_t iters, const uint32_t *consts, long long *c
     // operands come from memory so that they live in registers (kernel parameters would be re-read with LDC)
     const uint32_t k1 = consts[0], k2 = consts[1], k3 = consts[2];
     __shared__ uint4 sm[kThreads];
-    uint32_t v[kChains], e[kChains], f[kChains], b[kChains], d[kChains];
+    uint32_t v[kChains], e[kChains], f[kChains], b[kChains], d[kChains], g[kChains];
 #pragma unroll
     for (int c = 0; c < kChains; ++c) {
         v[c] = threadIdx.x * 0x10003u + c * k1;
@@ -96,6 +104,7 @@ probe_kernel(uint32_t *out, uint32_t iters, const uint32_t *consts, long long *c
         f[c] = v[c] + k3;
         b[c] = 0;
         d[c] = v[c] >> 3;
+        g[c] = v[c] >> 5;
     }
     sm[threadIdx.x] = make_uint4(v[0], v[1], v[2], v[3]);
     __syncthreads();
@@ -131,7 +140,23 @@ probe_kernel(uint32_t *out, uint32_t iters, const uint32_t *consts, long long *c
                     if (u & 1) b[c] = __vimax3_s16x2(b[c], d[c], h);
                     d[c] = v[c];
                     v[c] = h;
-                } else if (P == P_PAIR_DPX_IMAD) { v[c] = __viaddmax_s16x2(v[c], k1, k2); e[c] = imad_u(e[c], k1, k3); }
+                } else if (P == P_MIX_V2) {
+                    // the kernel's cell: PRMT, VIADD (ds), VIMNMX3.RELU (H), VIADD (open), VIADDMNMX x2 (E, F), VIMNMX3 / 2 (best)
+                    const uint32_t s = prmt(e[c], f[c], 0xc480 + (u & 3) * 0x1111);
+                    const uint32_t ds = __vadd2(d[c], s);
+                    const uint32_t h = __vimax3_s16x2_relu(ds, e[c], f[c]);
+                    const uint32_t open = __vadd2(h, k1);
+                    e[c] = __viaddmax_s16x2(e[c], k2, open);
+                    f[c] = __viaddmax_s16x2(f[c], k2, open);
+                    if (u & 1) b[c] = __vimax3_s16x2(b[c], g[c], ds);
+                    g[c] = ds;
+                    d[c] = v[c];
+                    v[c] = h;
+                } else if (P == P_PAIR_DPX_VIADD) { v[c] = __viaddmax_s16x2(v[c], k1, k2); e[c] = __vadd2(e[c], k3); }
+                else if (P == P_PAIR_DPX_HMNMX2) { v[c] = __viaddmax_s16x2(v[c], k1, k2); e[c] = (u & 1) ? hmax2_u(e[c], k3) : hmin2_u(e[c], f[c]); }
+                else if (P == P_PAIR_DPX_FFMA) { v[c] = __viaddmax_s16x2(v[c], k1, k2); e[c] = ffma_u(e[c], k1, k3); }
+                else if (P == P_PAIR_VIADD_IMAD) { v[c] = __vadd2(v[c], k1); e[c] = imad_u(e[c], k1, k3); }
+                else if (P == P_PAIR_DPX_IMAD) { v[c] = __viaddmax_s16x2(v[c], k1, k2); e[c] = imad_u(e[c], k1, k3); }
                 else if (P == P_PAIR_DPX_HFMA2) { v[c] = __viaddmax_s16x2(v[c], k1, k2); e[c] = hfma2_u(e[c], k1, k3); }
                 else if (P == P_PAIR_DPX_PRMT) { v[c] = __viaddmax_s16x2(v[c], k1, k2); e[c] = __byte_perm(e[c], k3, f[c]); }
                 else if (P == P_PAIR_DPX_IDP) { v[c] = __viaddmax_s16x2(v[c], k1, k2); e[c] = __dp4a((int)e[c], (int)k1, (int)k3); }
@@ -150,7 +175,7 @@ probe_kernel(uint32_t *out, uint32_t iters, const uint32_t *consts, long long *c
     const long long t1 = clock64();
     uint32_t acc = 0;
 #pragma unroll
-    for (int c = 0; c < kChains; ++c) acc ^= v[c] ^ e[c] ^ f[c] ^ b[c] ^ d[c];
+    for (int c = 0; c < kChains; ++c) acc ^= v[c] ^ e[c] ^ f[c] ^ b[c] ^ d[c] ^ g[c];
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }

@@ -81,6 +81,7 @@ struct Lane16 {
     static __device__ __forceinline__ reg add(reg a, reg b) { return __vadd2(a, b); }
     static __device__ __forceinline__ reg max2(reg a, reg b) { return __vmaxs2(a, b); }
     static __device__ __forceinline__ reg max3(reg a, reg b, reg c) { return __vimax3_s16x2(a, b, c); }
+    static __device__ __forceinline__ reg max3_relu(reg a, reg b, reg c) { return __vimax3_s16x2_relu(a, b, c); }
     // substitution scores of row byte B for the two sequences: {sext16(w_hi.b[B]), sext16(w_lo.b[B])}
     template <int B>
     static __device__ __forceinline__ reg score(uint32_t w_lo, uint32_t w_hi)
@@ -99,6 +100,7 @@ struct Lane32 {
     static __device__ __forceinline__ reg add(reg a, reg b) { return a + b; }
     static __device__ __forceinline__ reg max2(reg a, reg b) { return max(a, b); }
     static __device__ __forceinline__ reg max3(reg a, reg b, reg c) { return __vimax3_s32(a, b, c); }
+    static __device__ __forceinline__ reg max3_relu(reg a, reg b, reg c) { return __vimax3_s32_relu(a, b, c); }
     template <int B>
     static __device__ __forceinline__ reg score(uint32_t w_lo, uint32_t)
     {

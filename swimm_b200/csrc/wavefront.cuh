@@ -132,7 +132,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
                     }
                 }
 
-                reg hprev = L::splat(0);
+                // One cell per row.  ds = H(i-1,j-1) + S is a plain packed add (VIADD.16x2 does not occupy the
+                // ALU pipe) so that H = max(ds, E, F, 0) is ONE ALU instruction (VIMNMX3.RELU); the running best
+                // is taken over ds instead of H -- the same maximum, because E and F only ever hold earlier H values
+                // minus gap penalties -- which also keeps ptxas from fusing the add back into VIADDMNMX.
+                reg dsprev = L::splat(0);
 #pragma unroll
                 for (int x = 0; x < K; ++x) {
                     reg s;
@@ -142,16 +146,16 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
                         case 2: s = L::template score<2>(w1[x >> 2], w2[x >> 2]); break;
                         default: s = L::template score<3>(w1[x >> 2], w2[x >> 2]); break;
                     }
-                    const reg a = L::addmax(diag, s, E[x]);        // max(H(i-1,j-1) + S, E(i,j))
-                    const reg h = L::max_relu(a, f);               // max(.., F(i,j), 0)
+                    const reg ds = L::add(diag, s);                // H(i-1,j-1) + S
+                    const reg h = L::max3_relu(ds, E[x], f);       // max(ds, E(i,j), F(i,j), 0)
                     diag = H[x];
                     H[x] = h;
                     const reg open = L::add(h, ngoe);              // H(i,j) - (go+ge)
                     E[x] = L::addmax(E[x], nge, open);             // E(i,j+1)
                     f = L::addmax(f, nge, open);                   // F(i+1,j)
-                    if (x & 1) best = L::max3(best, hprev, h);
-                    else if (x == K - 1) best = L::max2(best, h);
-                    hprev = h;
+                    if (x & 1) best = L::max3(best, dsprev, ds);
+                    else if (x == K - 1) best = L::max2(best, ds);
+                    dsprev = ds;
                 }
                 out_h = H[K - 1];
                 out_f = f;
