@@ -255,6 +255,7 @@ def main():
     barrier()
     sampler.start()
     dev_s, search_s, topr_s, launches = 0.0, 0.0, 0.0, 0
+    q_secs = np.zeros(q.n)
     w0 = time.time()
     for _ in range(args.steps):
         step_resident()
@@ -263,6 +264,7 @@ def main():
         search_s += st["search_seconds"]
         topr_s += st["topr_seconds"]
         launches += st["launches"]
+        q_secs += s.query_seconds()
     barrier()
     wall_s = time.time() - w0
     sampler.stop_flag.set()
@@ -341,7 +343,9 @@ def main():
             "roofline": roof, "cpu_baseline": cpu_base,
             "detail": {"search_ms_per_step": search_s / args.steps * 1e3, "topr_ms_per_step": topr_s / args.steps * 1e3,
                        "wall_ms_per_step": wall_max / args.steps * 1e3, "db_load_seconds": db_load_s,
-                       "rescored_lanes": int(rescored), "db_bytes": int(st0["db_bytes"])}}
+                       "rescored_lanes": int(rescored), "db_bytes": int(st0["db_bytes"]),
+                       "per_query_gcups": {str(int(ql[i])): round(float(ql[i]) * len(dc) * args.steps / q_secs[i] / 1e9, 1)
+                                           for i in range(q.n) if q_secs[i] > 0}}}
     if world > 1:
         dist.destroy_process_group()
     print(json.dumps(line), flush=True)

@@ -102,6 +102,8 @@ int swg_gpu_fetch(swg_ctx *ctx, int32_t *scores, uint64_t *top_keys);   /* wait 
 int swg_gpu_sync(swg_ctx *ctx);                                   /* wait only */
 
 int swg_gpu_get_stats(swg_ctx *ctx, swg_stats *out);
+/* device time (CUDA events) of each query's kernels in the last completed run, in the order the queries were given */
+int swg_gpu_get_query_seconds(swg_ctx *ctx, double *seconds, uint64_t max_queries);
 
 /* Measured issue rates of the search kernel's instruction mix (the integer roofline the search is
  * reported against).  ginstr_per_s[p] = 1e9 thread-instructions per second on the whole GPU for probe p,

@@ -84,6 +84,8 @@ struct swg_ctx {
     // work buffers
     DeviceBuf d_scores, d_profile, d_profile32, d_boundary, d_counters, d_resc_list, d_topk_scratch, d_top_out;
     std::vector<uint32_t> h_counters;
+    std::vector<cudaEvent_t> q_events;      // q_count + 1 marks around every query's kernels
+    std::vector<double> q_seconds;
     uint64_t run_top = 0, run_top_stride = 0;
     bool run_done = false, run_kept_scores = false;
 
@@ -334,6 +336,7 @@ void swg_gpu_destroy(swg_ctx *ctx)
     ctx->d_resc_list.release();
     ctx->d_topk_scratch.release();
     ctx->d_top_out.release();
+    for (cudaEvent_t ev : ctx->q_events) cudaEventDestroy(ev);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_search_end) cudaEventDestroy(ctx->ev_search_end);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
@@ -628,6 +631,12 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     p.gap_open_extend = ctx->open_gap + ctx->extend_gap;
     p.gap_extend = ctx->extend_gap;
 
+    while (ctx->q_events.size() < nq + 1) {
+        cudaEvent_t ev;
+        SWG_CUDA(ctx, cudaEventCreate(&ev));
+        ctx->q_events.push_back(ev);
+    }
+    SWG_CUDA(ctx, cudaEventRecord(ctx->q_events[0], ctx->stream));
     uint64_t padded = 0;
     for (uint64_t q = 0; q < nq && ctx->ntiles; ++q) {
         const uint32_t m = ctx->q_len[q];
@@ -681,6 +690,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             ctx->stats.launches += 1;
         }
         if (e != cudaSuccess) return cuda_fail(ctx, e, "search kernel launch");
+        SWG_CUDA(ctx, cudaEventRecord(ctx->q_events[q + 1], ctx->stream));
         ctx->stats.cells += (uint64_t)m * ctx->local_residues;
         padded += (uint64_t)main_cfg.passes * main_cfg.G * main_cfg.K *
                   (uint64_t)((ctx->avg_cols + main_cfg.G - 1) * main_tiles) * kTileSeqs;
@@ -712,6 +722,12 @@ int swg_gpu_sync(swg_ctx *ctx)
         ctx->stats.device_seconds = ms_all * 1e-3;
         ctx->stats.search_seconds = ms_search * 1e-3;
         ctx->stats.topr_seconds = (ms_all - ms_search) * 1e-3;
+        ctx->q_seconds.assign(ctx->q_count, 0.0);
+        for (uint64_t q = 0; q < ctx->q_count && ctx->ntiles; ++q) {
+            float ms = 0.f;
+            SWG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->q_events[q], ctx->q_events[q + 1]));
+            ctx->q_seconds[q] = ms * 1e-3;
+        }
     }
     return SWG_OK;
 }
@@ -775,6 +791,13 @@ int swg_gpu_get_stats(swg_ctx *ctx, swg_stats *out)
 {
     if (!ctx || !out) return fail(ctx, SWG_ERR_ARG, "NULL argument");
     *out = ctx->stats;
+    return SWG_OK;
+}
+
+int swg_gpu_get_query_seconds(swg_ctx *ctx, double *seconds, uint64_t max_queries)
+{
+    if (!ctx || !seconds) return fail(ctx, SWG_ERR_ARG, "NULL argument");
+    for (uint64_t q = 0; q < max_queries; ++q) seconds[q] = q < ctx->q_seconds.size() ? ctx->q_seconds[q] : 0.0;
     return SWG_OK;
 }
 

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libswimm_cuda.so")
 ABI_SYMBOLS = [
     "swg_gpu_device_count", "swg_gpu_create", "swg_gpu_destroy", "swg_gpu_last_error", "swg_gpu_load_db",
     "swg_gpu_load_db_shard", "swg_gpu_load_db_interleaved", "swg_gpu_db_local_sequences", "swg_gpu_db_local_residues", "swg_gpu_search",
-    "swg_gpu_set_queries", "swg_gpu_run", "swg_gpu_fetch", "swg_gpu_sync", "swg_gpu_get_stats", "swg_gpu_pipebench",
+    "swg_gpu_set_queries", "swg_gpu_run", "swg_gpu_fetch", "swg_gpu_sync", "swg_gpu_get_stats", "swg_gpu_get_query_seconds", "swg_gpu_pipebench",
     "swg_gpu_set_option", "swg_gpu_debug_read", "swimm_gpu_search_avx2_compat",
 ]
 
@@ -67,6 +67,7 @@ def load_library() -> C.CDLL:
     L.swg_gpu_fetch.argtypes = [vp, vp, vp]
     L.swg_gpu_sync.argtypes = [vp]
     L.swg_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.swg_gpu_get_query_seconds.argtypes = [vp, vp, u64]
     L.swg_gpu_pipebench.argtypes = [vp, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.swg_gpu_debug_read.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     L.swg_gpu_set_option.argtypes = [vp, C.c_char_p, C.c_long]
@@ -200,6 +201,11 @@ class GpuSearch:
         s = Stats()
         self._check(self.L.swg_gpu_get_stats(self.ctx, C.byref(s)), "get_stats")
         return s.as_dict()
+
+    def query_seconds(self) -> np.ndarray:
+        out = np.zeros(self.q_count, dtype=np.float64)
+        self._check(self.L.swg_gpu_get_query_seconds(self.ctx, out.ctypes.data, self.q_count), "get_query_seconds")
+        return out
 
     def debug_read(self, name: str, dtype=np.uint8) -> np.ndarray:
         n = C.c_uint64(0)
