@@ -224,3 +224,33 @@ def test_round_trip_properties_at_scale(gpu):
     # numpy check of the top-10 against the full score vector
     order = np.lexsort((-np.arange(len(dl)), -scores[0].astype(np.int64)))[:10]
     assert np.array_equal(ki, order)
+
+
+@pytest.mark.parametrize("name", ["basic", "edge"])
+def test_cli_search_prints_the_reference_hit_lists(tmp_path, name):
+    """`swimm -S preprocess` + `swimm -S search -m 3` (the C host driving the C ABI): the printed hit lists
+    equal the ones the unmodified reference printed for the same FASTA files (tests/golden/*.json)."""
+    import json
+    import os
+    import re
+    import subprocess
+    from tests.helpers import GOLDEN, ROOT
+    exe = os.path.join(ROOT, "swimm_b200", "swimm")
+    prefix = str(tmp_path / "db")
+    subprocess.run([exe, "-S", "preprocess", "-i", os.path.join(GOLDEN, name + ".db.fasta"), "-o", prefix], check=True,
+                   stdout=subprocess.DEVNULL)
+    meta = json.load(open(os.path.join(GOLDEN, name + ".json")))
+    run = meta["runs"][0]
+    out = subprocess.run([exe, "-S", "search", "-q", os.path.join(GOLDEN, name + ".q.fasta"), "-d", prefix, "-m", "3",
+                          "-r", str(meta["n"]), "-s", run["matrix"], "-g", str(run["go"]), "-e", str(run["ge"])],
+                         check=True, capture_output=True, text=True).stdout
+    queries, cur = [], None
+    for line in out.split("\n"):
+        if line.startswith("Query no."):
+            cur = []
+            queries.append(cur)
+        m = re.match(r"^(-?\d+)\t.*syn\|(\d+)\|", line)
+        if m and cur is not None:
+            cur.append([int(m.group(1)), int(m.group(2))])
+    assert queries == run["hits"]
+    assert "Search speed:" in out and "Execution mode:\t\t\tB200 GPU only (1 GPU" in out
