@@ -198,6 +198,8 @@ cudaError_t launch_wavefront(bool lane32, const Config &cfg, int grid, cudaStrea
 {
     if (cfg.global_profile) return lane32 ? launch_wf_l32_gp(grid, stream, p) : launch_wf_l16_gp(grid, stream, p);
     const size_t smem = (size_t)cfg.passes * kPassBytes;
+    if (cfg.passes > 1) return lane32 ? launch_wf_l32_g32_mp(cfg.K, grid, smem, stream, p)
+                                      : launch_wf_l16_g32_mp(cfg.K, grid, smem, stream, p);
     if (lane32) return launch_wf_l32_g32(cfg.K, grid, smem, stream, p);
     switch (cfg.G) {
         case 4: return launch_wf_l16_g4(cfg.K, grid, smem, stream, p);
@@ -606,7 +608,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     SWG_CUDA(ctx, ctx->d_scores.reserve(std::max<uint64_t>(nq * n_pad, 1) * sizeof(int32_t)));
     SWG_CUDA(ctx, ctx->d_profile.reserve((size_t)max_passes * kPassBytes));
     SWG_CUDA(ctx, ctx->d_profile32.reserve((size_t)max_passes * kPassBytes));
-    SWG_CUDA(ctx, ctx->d_boundary.reserve(warps * ctx->maxcols * sizeof(uint2)));
+    SWG_CUDA(ctx, ctx->d_boundary.reserve(warps * (size_t)(ctx->maxcols + kBoundarySlack) * sizeof(uint2)));
     SWG_CUDA(ctx, ctx->d_counters.reserve(std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t)));
     SWG_CUDA(ctx, ctx->d_resc_list.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
     const TopkPlan tp = topk_plan(n_pad, top, nq);
@@ -626,7 +628,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     p.shard = ctx->shard;
     p.num_shards = ctx->num_shards;
     p.boundary = ctx->d_boundary.as<uint2>();
-    p.maxcols = ctx->maxcols;
+    p.maxcols = ctx->maxcols + kBoundarySlack;      // stride of a warp's scratch line (multiple of 8)
     p.resc_list = ctx->d_resc_list.as<uint32_t>();
     p.gap_open_extend = ctx->open_gap + ctx->extend_gap;
     p.gap_extend = ctx->extend_gap;

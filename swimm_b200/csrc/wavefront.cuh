@@ -1,38 +1,59 @@
 // wavefront.cuh -- the Smith-Waterman search kernel of the B200 build (replaces the reference's
 // cpu_search_avx2_sp inner loops, CPUsearch.c:553-956).
 //
-// Parallelisation (inter-task across groups, wavefront inside a group):
+// Parallelisation (inter-task across groups, anti-diagonal wavefront inside a group):
 //   * a GROUP of G threads (G = 4, 8, 16 or 32 lanes of one warp) aligns the query against one PAIR of
 //     database sequences; the two sequences live in the two 16-bit halves of every register (Lane16) and
-//     are advanced by single DPX instructions (VIADDMNMX.S16x2, VIMNMX.S16x2.RELU, VIMNMX3.S16x2);
-//   * thread t of the group owns query rows [t*K, (t+1)*K) of the current pass, H and E of those rows
-//     stay in registers; database columns stream through the group as a systolic pipeline: at step s
-//     thread t works on column s - t and hands (H, F) of its last row plus the column's profile
-//     offsets to thread t + 1 with warp shuffles;
-//   * queries longer than G*K rows take several passes; the last row of a pass is parked in a
-//     per-warp global scratch line (L2 resident) and re-enters at thread 0 of the next pass.
-// Per cell pair the recurrence costs 6 integer-pipe instructions plus one PRMT that packs the two
-// substitution scores fetched from the shared-memory query profile.
+//     are advanced by single packed instructions (VIMNMX3.S16x2.RELU, VIADDMNMX.S16x2, VIADD.16x2);
+//   * thread t of the group owns query rows [t*K, (t+1)*K) of the current pass; H and E of those rows stay in
+//     registers; database columns stream through the group as a systolic pipeline: at step s thread t works
+//     on column s - t and hands (H, F) of its last row plus the column's profile offsets to thread t + 1
+//     with warp shuffles;
+//   * the pipeline never drains between sequences: when thread 0 has fed the last column of one segment
+//     (a pass of a task) it feeds the first column of the next one; a "new segment" mark travels down the
+//     pipeline with the column and each thread resets its rows when the mark reaches it.  A task's score is
+//     reduced and stored a few loop trips later, when the mark of the following task has passed every thread;
+//   * queries longer than G*K rows take several passes; the last row of a pass is parked in a per-warp
+//     global scratch line (L2 resident) and re-enters at thread 0 in the next pass.
 //
-// Exactness: lanes use wrapping 16-bit adds.  A lane whose running best reaches kOverflow16 is
-// reported in resc_list and recomputed by the Lane32 instantiation, so every stored score is the
-// exact int32 value, like the reference's 8 -> 16 -> 32 bit escalation (CPUsearch.c:678-956).
+// Per cell pair the recurrence is 4.5 ALU-pipe instructions (PRMT score pack, VIMNMX3.RELU for H, two
+// VIADDMNMX for E and F, half a VIMNMX3 for the running best) plus two VIADD.16x2, which issue on the
+// FMA-heavy pipe and overlap the ALU pipe completely (pipebench: pair_viaddmnmx_viadd16x2 = 126/clk/SM).
+//
+// Exactness: lanes use wrapping 16-bit adds.  A lane whose running best reaches kOverflow16 is reported in
+// resc_list and recomputed by the Lane32 instantiation, so every stored score is the exact int32 value, like
+// the reference's 8 -> 16 -> 32 bit escalation (CPUsearch.c:678-956).
 #pragma once
 
 #include "swg_common.cuh"
 
 namespace swg {
 
-template <class L, int G, int K, bool GP>
+// A column travels down the pipeline as one 32-bit word:
+//   bits 15:8  = 4 * residue code of sequence A  (so that word & 0xff00 is the profile offset code * 1024)
+//   bits 31:24 = 4 * residue code of sequence B
+//   bits 23:16 = pass of the segment the column belongs to (selects the 25 KB profile slice)
+//   bits  2:0  = marks
+constexpr uint32_t kMarkSegment = 1u;   // first column of a segment: the rows restart from H = E = 0
+constexpr uint32_t kMarkTask = 2u;      // ... and it is the first pass of a new task: the running best is parked
+constexpr uint32_t kMarkCarry = 4u;     // the segment is not the task's last pass: the last row goes to the scratch line
+
+template <class L, int G, int K, bool MP, bool GP>
 __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfParams p)
 {
     typedef typename L::reg reg;
     static_assert(G == 4 || G == 8 || G == 16 || G == 32, "group size");
     static_assert(K >= 1 && K <= kMaxRowsPerThread, "rows per thread");
     static_assert(L::kSeqs == 2 || G == 32, "the 32-bit kernel runs one sequence per warp");
+    static_assert(!MP || G == 32, "several passes need one pair per warp (the scratch line is per warp)");
+    static_assert(!GP || MP, "the global-profile variant is a multi-pass kernel");
     constexpr int GPW = 32 / G;                       // groups per warp
     constexpr int TPT = (L::kSeqs == 2) ? (kTilePairs / GPW) : 1;   // warp tasks per tile
     constexpr int KCH = (K + 15) / 16;                // 16-row profile chunks per thread
+    constexpr int NC = kTripCols;                     // columns per loop trip
+    constexpr uint32_t FI = G / NC;                   // trip of the NEXT task at which a finished task is stored
+    constexpr uint32_t kMinTrips = FI + 4;            // every segment is at least this long (padding columns)
+    static_assert(kMinTrips * NC <= kBoundarySlack, "scratch line too short for padded segments");
 
     // GP ("global profile"): queries with more passes than fit in shared memory read the profile through L1
     extern __shared__ __align__(16) uint8_t prof_smem[];
@@ -53,143 +74,114 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
     uint2 *bnd = p.boundary + (size_t)warp_global * p.maxcols;
     const reg nge = L::splat(-p.gap_extend);
     const reg ngoe = L::splat(-p.gap_open_extend);
+    const uint32_t npass = MP ? p.passes : 1u;
+    const uint32_t pad_pk = (L::kSeqs == 2) ? 0x60006000u : 0x00006000u;
+    const uint8_t *prof_t = prof + t * 16;
 
     uint32_t ntasks;
     if (L::kSeqs == 2) ntasks = p.tile_count * TPT;
     else ntasks = *p.resc_count;
 
-    for (;;) {
+    auto fetch_task = [&]() -> uint32_t {
         uint32_t task = 0;
         if (lane == 0) task = atomicAdd(p.task_counter, 1u);
-        task = __shfl_sync(0xffffffffu, task, 0);
-        if (task >= ntasks) break;
+        return __shfl_sync(0xffffffffu, task, 0);
+    };
 
-        uint32_t tile, pair, half = 0, lseq;
-        if (L::kSeqs == 2) {
-            tile = p.tile_first + p.tile_count - 1 - task / TPT;        // longest tiles first
-            pair = (task % TPT) * GPW + g;
-            lseq = tile * kTileSeqs + 2 * pair;
-        } else {
-            lseq = p.resc_list[task];
-            tile = lseq / kTileSeqs;
-            pair = (lseq % kTileSeqs) >> 1;
-            half = lseq & 1u;
+    // ---- per-thread pipeline state ----
+    // DS[x] = H(i-1, j) + S(i, j+1): the diagonal term of row x for the column this thread processes NEXT.
+    // It is formed one column ahead (the profile words loaded in a step are those of the next column), which
+    // makes every row slot a plain read-then-overwrite and keeps the hot loop free of register moves.
+    reg DS[K], E[K];
+#pragma unroll
+    for (int x = 0; x < K; ++x) { DS[x] = L::splat(0); E[x] = L::splat(0); }
+    reg best = L::splat(0), bsave = L::splat(0);
+    reg out_h = L::splat(0), out_f = L::splat(0);
+    uint32_t pk = pad_pk;             // the column word received last (= of the column processed in the next step)
+
+    // One step of this thread: process the column whose word arrived in the previous step, using (H, F) of the
+    // row above handed down now, and prepare DS for the column whose word arrives now.
+    auto column = [&](uint32_t in_pkn, uint2 in_hf, uint32_t store_col) {
+        uint32_t pkn = __shfl_up_sync(0xffffffffu, pk, 1, G);
+        reg r_h = (reg)__shfl_up_sync(0xffffffffu, out_h, 1, G);
+        reg r_f = (reg)__shfl_up_sync(0xffffffffu, out_f, 1, G);
+        if (t == 0) {
+            pkn = in_pkn;
+            r_h = MP ? (reg)in_hf.x : L::splat(0);
+            r_f = MP ? (reg)in_hf.y : L::splat(0);
         }
-        const uint32_t ncols = p.tile_cols[tile];
-        const uint32_t *words = reinterpret_cast<const uint32_t *>(p.db + p.tile_off[tile] + pair);
-        const uint32_t niter = (ncols + G) >> 1;        // two columns per iteration, ncols + G - 1 steps
-        // PRMT selectors that turn a residue byte (code*4) into the profile offset code*1024
-        const uint32_t selA = (L::kSeqs == 2) ? 0x1404u : (0x4404u | (half << 4));
-        const uint32_t selB = (L::kSeqs == 2) ? 0x3424u : (0x4404u | ((2u + half) << 4));
-        const uint32_t pad_pk = (L::kSeqs == 2) ? 0x60006000u : 0x00006000u;
+        const uint32_t pk_cur = pk;
+        pk = pkn;
 
-        reg best = L::splat(0);
-
-        for (uint32_t pass = 0; pass < p.passes; ++pass) {
-            reg H[K], E[K];
+        // profile words of the NEXT column
+        uint32_t w1[KCH * 4], w2[KCH * 4];
+        {
+            const uint32_t hi = pkn >> 16;
+            const uint8_t *pb = MP ? prof_t + (hi & 0xffu) * kPassBytes : prof_t;
+            const uint4 *q1 = reinterpret_cast<const uint4 *>(pb + (pkn & 0xff00u));
 #pragma unroll
-            for (int x = 0; x < K; ++x) { H[x] = L::splat(0); E[x] = L::splat(0); }
-            reg out_h = L::splat(0), out_f = L::splat(0), up_prev = L::splat(0);
-            uint32_t pk = pad_pk;
-            const uint8_t *pbase = prof + pass * kPassBytes + t * 16;
-            const bool carry_in = pass > 0;
-            const bool carry_out = (pass + 1 < p.passes) && (t == G - 1);
-
-            // thread 0's inputs for columns (0, 1)
-            uint32_t word = words[0];
-            uint2 b0 = make_uint2(0u, 0u), b1 = make_uint2(0u, 0u);
-            if (carry_in && t == 0) { b0 = __ldcg(bnd); b1 = __ldcg(bnd + 1); }
-
-            auto column = [&](uint32_t in_pk, reg in_h, reg in_f, int col_out) {
-                // receive from the thread above (it finished this column one step ago)
-                uint32_t r_pk = __shfl_up_sync(0xffffffffu, pk, 1, G);
-                reg r_h = (reg)__shfl_up_sync(0xffffffffu, out_h, 1, G);
-                reg r_f = (reg)__shfl_up_sync(0xffffffffu, out_f, 1, G);
-                if (t == 0) { r_pk = in_pk; r_h = in_h; r_f = in_f; }
-                pk = r_pk;
-                reg diag = up_prev;
-                up_prev = r_h;
-                reg f = r_f;
-
-                uint32_t w1[KCH * 4], w2[KCH * 4];
-                {
-                    const uint4 *q1 = reinterpret_cast<const uint4 *>(pbase + (pk & 0xffffu));
-#pragma unroll
-                    for (int i = 0; i < KCH; ++i) {
-                        const uint4 v = q1[i * G];
-                        w1[4 * i] = v.x; w1[4 * i + 1] = v.y; w1[4 * i + 2] = v.z; w1[4 * i + 3] = v.w;
-                    }
-                    if (L::kSeqs == 2) {
-                        const uint4 *q2 = reinterpret_cast<const uint4 *>(pbase + (pk >> 16));
-#pragma unroll
-                        for (int i = 0; i < KCH; ++i) {
-                            const uint4 v = q2[i * G];
-                            w2[4 * i] = v.x; w2[4 * i + 1] = v.y; w2[4 * i + 2] = v.z; w2[4 * i + 3] = v.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < KCH * 4; ++i) w2[i] = 0u;
-                    }
-                }
-
-                // One cell per row.  ds = H(i-1,j-1) + S is a plain packed add (VIADD.16x2 does not occupy the
-                // ALU pipe) so that H = max(ds, E, F, 0) is ONE ALU instruction (VIMNMX3.RELU); the running best
-                // is taken over ds instead of H -- the same maximum, because E and F only ever hold earlier H values
-                // minus gap penalties -- which also keeps ptxas from fusing the add back into VIADDMNMX.
-                reg dsprev = L::splat(0);
-#pragma unroll
-                for (int x = 0; x < K; ++x) {
-                    reg s;
-                    switch (x & 3) {
-                        case 0: s = L::template score<0>(w1[x >> 2], w2[x >> 2]); break;
-                        case 1: s = L::template score<1>(w1[x >> 2], w2[x >> 2]); break;
-                        case 2: s = L::template score<2>(w1[x >> 2], w2[x >> 2]); break;
-                        default: s = L::template score<3>(w1[x >> 2], w2[x >> 2]); break;
-                    }
-                    const reg ds = L::add(diag, s);                // H(i-1,j-1) + S
-                    const reg h = L::max3_relu(ds, E[x], f);       // max(ds, E(i,j), F(i,j), 0)
-                    diag = H[x];
-                    H[x] = h;
-                    const reg open = L::add(h, ngoe);              // H(i,j) - (go+ge)
-                    E[x] = L::addmax(E[x], nge, open);             // E(i,j+1)
-                    f = L::addmax(f, nge, open);                   // F(i+1,j)
-                    if (x & 1) best = L::max3(best, dsprev, ds);
-                    else if (x == K - 1) best = L::max2(best, ds);
-                    dsprev = ds;
-                }
-                out_h = H[K - 1];
-                out_f = f;
-                if (carry_out && col_out >= 0 && col_out < (int)ncols)
-                    bnd[col_out] = make_uint2((uint32_t)out_h, (uint32_t)out_f);
-            };
-
-            for (uint32_t it = 0; it < niter; ++it) {
-                const uint32_t c0 = 2 * it;                 // thread 0's columns this iteration: c0, c0 + 1
-                // prefetch thread 0's inputs for the next iteration
-                uint32_t nword = kPadWord;
-                uint2 nb0 = make_uint2(0u, 0u), nb1 = make_uint2(0u, 0u);
-                const uint32_t cn = c0 + 2;
-                if (cn < ncols) {
-                    nword = words[(cn >> 3) * (kTilePairs * 4) + ((cn & 7u) >> 1)];
-                    if (carry_in && t == 0) { nb0 = __ldcg(bnd + cn); nb1 = __ldcg(bnd + cn + 1); }
-                }
-                const uint32_t pkA = __byte_perm(word, 0u, selA);
-                const uint32_t pkB = __byte_perm(word, 0u, selB);
-                column(pkA, (reg)b0.x, (reg)b0.y, (int)c0 - (G - 1));
-                column(pkB, (reg)b1.x, (reg)b1.y, (int)c0 + 1 - (G - 1));
-                word = nword; b0 = nb0; b1 = nb1;
+            for (int i = 0; i < KCH; ++i) {
+                const uint4 v = q1[i * G];
+                w1[4 * i] = v.x; w1[4 * i + 1] = v.y; w1[4 * i + 2] = v.z; w1[4 * i + 3] = v.w;
             }
-            if (p.passes > 1) { __threadfence_block(); __syncwarp(); }
-        }
-
-        // best over the rows of the group
+            if (L::kSeqs == 2) {
+                const uint4 *q2 = reinterpret_cast<const uint4 *>(pb + (hi & 0xff00u));
 #pragma unroll
-        for (int o = G >> 1; o > 0; o >>= 1)
-            best = L::max2(best, (reg)__shfl_xor_sync(0xffffffffu, best, o, G));
+                for (int i = 0; i < KCH; ++i) {
+                    const uint4 v = q2[i * G];
+                    w2[4 * i] = v.x; w2[4 * i + 1] = v.y; w2[4 * i + 2] = v.z; w2[4 * i + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < KCH * 4; ++i) w2[i] = 0u;
+            }
+        }
+        auto score_of = [&](int x) -> reg {
+            switch (x & 3) {
+                case 0: return L::template score<0>(w1[x >> 2], w2[x >> 2]);
+                case 1: return L::template score<1>(w1[x >> 2], w2[x >> 2]);
+                case 2: return L::template score<2>(w1[x >> 2], w2[x >> 2]);
+                default: return L::template score<3>(w1[x >> 2], w2[x >> 2]);
+            }
+        };
 
+        // One cell per row: 4.5 ALU-pipe instructions (PRMT, VIMNMX3.RELU, 2 x VIADDMNMX, VIMNMX3 / 2) and two
+        // VIADD.16x2 on the FMA-heavy pipe.  H = max(ds, E, F, 0) is ONE instruction because ds is formed by a
+        // separate add; the running best is taken over ds instead of H -- the same maximum, since E and F only
+        // ever hold earlier H values minus gap penalties.
+        reg hp = r_h, f = r_f, dsprev = L::splat(0);
+#pragma unroll
+        for (int x = 0; x < K; ++x) {
+            const reg ds = DS[x];
+            const reg h = L::max3_relu(ds, E[x], f);       // max(ds, E(i,j), F(i,j), 0)
+            const reg open = L::add(h, ngoe);              // H(i,j) - (go+ge)
+            E[x] = L::addmax(E[x], nge, open);             // E(i,j+1)
+            f = L::addmax(f, nge, open);                   // F(i+1,j)
+            if (x & 1) best = L::max3(best, dsprev, ds);
+            else if (x == K - 1) best = L::max2(best, ds);
+            dsprev = ds;
+            DS[x] = L::add(hp, score_of(x));               // H(i-1,j) + S(i,j+1)
+            hp = h;
+        }
+        out_h = hp;
+        out_f = f;
+        if (MP && t == G - 1 && (pk_cur & kMarkCarry))
+            bnd[store_col] = make_uint2((uint32_t)out_h, (uint32_t)out_f);
+        if (pkn & kMarkSegment) {          // rare and divergent: the next column starts a segment
+#pragma unroll
+            for (int x = 0; x < K; ++x) { DS[x] = score_of(x); E[x] = L::splat(0); }
+            if (pkn & kMarkTask) { bsave = best; best = L::splat(0); }
+        }
+    };
+
+    // Store the scores of a task whose last column has left the pipeline (all threads hold its best in bsave).
+    auto finalize = [&](uint32_t lseq) {
+        reg b = bsave;
+#pragma unroll
+        for (int o = G >> 1; o > 0; o >>= 1) b = L::max2(b, (reg)__shfl_xor_sync(0xffffffffu, b, o, G));
         if (t == 0) {
             if (L::kSeqs == 2) {
-                const uint32_t bb = (uint32_t)best;
+                const uint32_t bb = (uint32_t)b;
                 const int s_lo = (int)(short)(bb & 0xffffu), s_hi = (int)(short)(bb >> 16);
                 if (global_seq_index(p, lseq) < p.n_total) {
                     p.scores[lseq] = s_lo;
@@ -200,9 +192,90 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
                     if (s_hi >= kOverflow16) p.resc_list[atomicAdd(p.resc_count, 1u)] = lseq + 1;
                 }
             } else {
-                p.scores[lseq] = (int32_t)best;
+                p.scores[lseq] = (int32_t)b;
             }
         }
+    };
+
+    bool pending = false;             // warp-uniform: a finished task waits for its store
+    uint32_t pend_lseq = 0;
+    uint32_t next_task = fetch_task();
+    uint2 hf_in = make_uint2(0u, 0u);   // thread 0: (H, F) entering the column it processes in the next step
+
+    for (;;) {
+        const uint32_t task = next_task;
+        const bool have = task < ntasks;
+        if (!have && !pending) break;
+        if (have) next_task = fetch_task();          // fetched one task ahead: the atomic's latency is hidden
+
+        // ---- decode the task (a flush segment of padding columns when there is none left) ----
+        uint32_t half = 0, lseq = 0, ncols = 0;
+        const uint2 *words = nullptr;
+        if (have) {
+            uint32_t tile, pair;
+            if (L::kSeqs == 2) {
+                tile = p.tile_first + p.tile_count - 1 - task / TPT;        // longest tiles first
+                pair = (task % TPT) * GPW + g;
+                lseq = tile * kTileSeqs + 2 * pair;
+            } else {
+                lseq = p.resc_list[task];
+                tile = lseq / kTileSeqs;
+                pair = (lseq % kTileSeqs) >> 1;
+                half = lseq & 1u;
+            }
+            ncols = p.tile_cols[tile];
+            words = reinterpret_cast<const uint2 *>(p.db + p.tile_off[tile] + pair);
+        }
+        const uint32_t data_trips = ncols / NC;
+        const uint32_t trips = data_trips < kMinTrips ? kMinTrips : data_trips;
+        const uint32_t seg_cols = trips * NC;
+        // PRMT selectors that turn a residue byte (code*4) into byte lanes 1 and 3 of the column word
+        const uint32_t selA = (L::kSeqs == 2) ? 0x1404u : (0x4404u | (half << 4));
+        const uint32_t selB = (L::kSeqs == 2) ? 0x3424u : (0x4404u | ((2u + half) << 4));
+        const uint32_t seg_passes = have ? npass : 1u;
+
+        for (uint32_t pass = 0; pass < seg_passes; ++pass) {
+            const uint32_t first_marks = kMarkSegment | (pass == 0 ? kMarkTask : 0u);
+            const uint32_t tag = MP ? ((pass << 16) | ((pass + 1 < seg_passes) ? kMarkCarry : 0u)) : 0u;
+            const bool carry_in = MP && pass > 0 && t == 0;
+
+            // thread 0 feeds the pipeline: four columns of the pair per trip (two 32-bit words), fetched one trip
+            // ahead, and -- after the first pass -- the (H, F) row parked by the previous pass, one column ahead
+            uint2 w = make_uint2(kPadWord, kPadWord);
+            if (t == 0 && data_trips > 0) w = words[0];
+            uint2 hf_next = make_uint2(0u, 0u);
+            if (carry_in) hf_next = __ldcg(bnd);
+#pragma unroll 1
+            for (uint32_t trip = 0; trip < trips; ++trip) {
+                if (pending && pass == 0 && trip == FI) { finalize(pend_lseq); pending = false; }
+                uint2 nw = make_uint2(kPadWord, kPadWord);
+                const uint32_t nt = trip + 1;
+                if (t == 0 && nt < data_trips) nw = words[(nt >> 1) * (kTilePairs * 2) + (nt & 1u)];
+                // The words of columns 4*trip .. 4*trip+3 enter now; the cells processed in these four steps are
+                // those of columns 4*trip-1 .. 4*trip+2.  Thread G-1 runs G-1 columns behind thread 0: its
+                // scratch-line column may still lie in the previous pass (same task, same length).
+                const uint32_t c0 = trip * NC;
+                uint32_t sc = c0 + seg_cols - G;
+                if (sc >= seg_cols) sc -= seg_cols;
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const uint32_t word = (j < 2) ? w.x : w.y;
+                    uint32_t pkn = prmt(word, 0u, (j & 1) ? selB : selA) | tag;
+                    if (j == 0 && trip == 0) pkn |= first_marks;
+                    const uint2 hf = hf_in;           // enters the column processed in this step (column c0 + j - 1)
+                    hf_in = hf_next;                  // enters column c0 + j
+                    if (MP) {
+                        hf_next = make_uint2(0u, 0u);
+                        if (carry_in && c0 + j + 1 < seg_cols) hf_next = __ldcg(bnd + c0 + j + 1);
+                    }
+                    column(pkn, hf, sc);
+                    if (MP) sc = (sc + 1 == seg_cols) ? 0u : sc + 1;
+                }
+                w = nw;
+                if (MP) __syncwarp();             // orders thread G-1's scratch-line stores before thread 0's later loads
+            }
+        }
+        if (have) { pending = true; pend_lseq = lseq; }
     }
 }
 
@@ -212,23 +285,26 @@ cudaError_t launch_wf_l16_g8(int K, int grid, size_t smem, cudaStream_t stream, 
 cudaError_t launch_wf_l16_g16(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
 cudaError_t launch_wf_l16_g32(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
 cudaError_t launch_wf_l32_g32(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
+// multi-pass variants (G = 32): the last row of a pass is carried to the next one through the scratch line
+cudaError_t launch_wf_l16_g32_mp(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
+cudaError_t launch_wf_l32_g32_mp(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p);
 // the two "profile in global memory" variants (G = 32, K = 32) for queries of more than kMaxSmemPasses passes
 cudaError_t launch_wf_l16_gp(int grid, cudaStream_t stream, const WfParams &p);
 cudaError_t launch_wf_l32_gp(int grid, cudaStream_t stream, const WfParams &p);
 
-template <class L, int G, int K, bool GP>
+template <class L, int G, int K, bool MP, bool GP>
 cudaError_t launch_one(int grid, size_t smem, cudaStream_t stream, const WfParams &p)
 {
     static size_t configured[64] = {0};            // per device: the attribute lives in the device's context
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(wavefront_kernel<L, G, K, GP>,
+        cudaError_t e = cudaFuncSetAttribute(wavefront_kernel<L, G, K, MP, GP>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = smem;
     }
-    wavefront_kernel<L, G, K, GP><<<grid, kBlockThreads, smem, stream>>>(p);
+    wavefront_kernel<L, G, K, MP, GP><<<grid, kBlockThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

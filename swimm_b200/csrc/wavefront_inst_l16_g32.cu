@@ -1,4 +1,4 @@
-// wavefront_inst_l16_g32.cu -- instantiations of wavefront_kernel<Lane16, 32, K> for K = 1..32 (one file per
+// wavefront_inst_l16_g32.cu -- instantiations of wavefront_kernel<Lane16, 32, K, false> for K = 1..32 (one file per
 // family so that the families compile in parallel).
 #include "wavefront.cuh"
 
@@ -7,7 +7,7 @@ namespace swg {
 cudaError_t launch_wf_l16_g32(int K, int grid, size_t smem, cudaStream_t stream, const WfParams &p)
 {
     switch (K) {
-#define SWG_CASE(k) case k: return launch_one<Lane16, 32, k, false>(grid, smem, stream, p);
+#define SWG_CASE(k) case k: return launch_one<Lane16, 32, k, false, false>(grid, smem, stream, p);
         SWG_CASE(1) SWG_CASE(2) SWG_CASE(3) SWG_CASE(4) SWG_CASE(5) SWG_CASE(6) SWG_CASE(7) SWG_CASE(8)
         SWG_CASE(9) SWG_CASE(10) SWG_CASE(11) SWG_CASE(12) SWG_CASE(13) SWG_CASE(14) SWG_CASE(15) SWG_CASE(16)
         SWG_CASE(17) SWG_CASE(18) SWG_CASE(19) SWG_CASE(20) SWG_CASE(21) SWG_CASE(22) SWG_CASE(23) SWG_CASE(24)
@@ -15,11 +15,6 @@ cudaError_t launch_wf_l16_g32(int K, int grid, size_t smem, cudaStream_t stream,
 #undef SWG_CASE
         default: return cudaErrorInvalidValue;
     }
-}
-
-cudaError_t launch_wf_l16_gp(int grid, cudaStream_t stream, const WfParams &p)
-{
-    return launch_one<Lane16, 32, 32, true>(grid, 0, stream, p);
 }
 
 }  // namespace swg
