@@ -21,7 +21,9 @@ using namespace swg;
 namespace {
 
 constexpr int kMaxSmemPasses = 8;            // 8 x 25 KB of query profile per CTA
-constexpr uint32_t kDefaultLongCols = 3072;  // tiles with more columns than this go to the 32-thread kernel
+constexpr uint32_t kDefaultLongCols = 3072;
+constexpr uint64_t kMaxLongBlocks = 12;
+constexpr double kSmHz = 1.9e9;              // SM clock assumed by the long-tile estimate      // SMs the long-tile launch may take while the main kernel runs  // tiles with more columns than this go to the 32-thread kernel
 
 struct Config {          // how one query is mapped onto thread groups
     int G, K;
@@ -58,7 +60,8 @@ struct swg_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_search_end = nullptr, ev_end = nullptr;
+    cudaStream_t side_stream = nullptr;      // carries the main search kernel while long tiles run on `stream`
+    cudaEvent_t ev_begin = nullptr, ev_search_end = nullptr, ev_end = nullptr, ev_fork = nullptr, ev_join = nullptr;
     char err[512] = {0};
 
     // resident database shard
@@ -140,21 +143,25 @@ int cuda_fail(swg_ctx *ctx, cudaError_t e, const char *what)
     } while (0)
 
 // ---- mapping a query onto thread groups ---------------------------------------------------------
-// Cost model (relative time per database column): the group computes passes * G * K rows of which m are
-// useful, every column step costs about kStepOverhead rows of bookkeeping (shuffles, profile fetch, loop),
-// and a sequence of L columns occupies the systolic pipeline for L + G - 1 steps.
-constexpr double kStepOverhead = 3.0;
+// The group computes passes * G * K rows of which m are useful; how fast a shape runs (per-column overhead,
+// pipeline skew, registers) was measured once per shape on a B200 (tools/calibrate.py -> swg_rates.inc).
+// The planner minimises rows / rate.
+#include "swg_rates.inc"
 
-double config_cost(uint32_t m, int G, int K, uint32_t passes, double avg_cols)
+double shape_rate(int G, int K, uint32_t passes)
 {
-    double c = (double)passes * G * (K + kStepOverhead) * (avg_cols + G - 1) / avg_cols;
-    if (G == 4) c *= 1.15;          // two groups share a quarter-warp: profile reads conflict 2-way
-    (void)m;
-    return c;
+    if (passes > 1) return kRateMulti_G32[K];
+    switch (G) {
+        case 4: return kRateSingle_G4[K];
+        case 8: return kRateSingle_G8[K];
+        case 16: return kRateSingle_G16[K];
+        default: return kRateSingle_G32[K];
+    }
 }
 
 Config choose_config(uint32_t m, double avg_cols, long force_group, long force_rows)
 {
+    (void)avg_cols;
     Config best = {32, 32, 1, false};
     if (m == 0) m = 1;
     double best_cost = 1e300;
@@ -165,11 +172,12 @@ Config choose_config(uint32_t m, double avg_cols, long force_group, long force_r
             const uint32_t rows = (uint32_t)(G * K);
             const uint32_t passes = (m + rows - 1) / rows;
             if (passes > 1 && G != 32) continue;     // the pass boundary line is per warp: one pair per warp
-            const double c = config_cost(m, G, K, passes, avg_cols);
+            if (passes > (uint32_t)kMaxSmemPasses && !(force_group || force_rows)) continue;
+            const double c = (double)passes * rows / shape_rate(G, K, passes);
             if (c < best_cost) { best_cost = c; best = {G, K, passes, passes > (uint32_t)kMaxSmemPasses}; }
         }
     }
-    if (best_cost == 1e300) {       // forced values that cannot hold the query: fall back to the widest shape
+    if (best_cost == 1e300) {       // nothing fits in shared memory (or forced values cannot hold the query)
         const uint32_t passes = (m + 1023) / 1024;
         best = {32, 32, passes, passes > (uint32_t)kMaxSmemPasses};
     }
@@ -309,7 +317,12 @@ int swg_gpu_create(int device, swg_ctx **out)
                     prop.major, prop.minor);
     }
     if (e == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_search_end);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_end);
@@ -326,6 +339,7 @@ void swg_gpu_destroy(swg_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_db(ctx);
     ctx->d_queries.release();
@@ -342,6 +356,9 @@ void swg_gpu_destroy(swg_ctx *ctx)
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_search_end) cudaEventDestroy(ctx->ev_search_end);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -352,7 +369,7 @@ int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value)
 {
     if (!ctx || !name) return fail(ctx, SWG_ERR_ARG, "NULL argument");
     if (!strcmp(name, "long_threshold")) {
-        if (value < 8) return fail(ctx, SWG_ERR_ARG, "long_threshold must be >= 8");
+        if (value != 0 && value < 8) return fail(ctx, SWG_ERR_ARG, "long_threshold must be 0 (automatic) or >= 8");
         ctx->long_cols = value;
         if (ctx->db_ready) {
             uint32_t fl = ctx->ntiles;
@@ -597,7 +614,8 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     ctx->stats.rescored = 0;
 
     const int grid = ctx->sm_count;
-    const size_t warps = (size_t)grid * (kBlockThreads / 32);
+    const int warps_per_block = kBlockThreads / 32;
+    const size_t warps = (size_t)grid * warps_per_block;
     std::vector<Config> main_cfgs(nq), wide_cfgs(nq);
     uint32_t max_passes = 1;
     for (uint64_t q = 0; q < nq; ++q) {
@@ -608,7 +626,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     SWG_CUDA(ctx, ctx->d_scores.reserve(std::max<uint64_t>(nq * n_pad, 1) * sizeof(int32_t)));
     SWG_CUDA(ctx, ctx->d_profile.reserve((size_t)max_passes * kPassBytes));
     SWG_CUDA(ctx, ctx->d_profile32.reserve((size_t)max_passes * kPassBytes));
-    SWG_CUDA(ctx, ctx->d_boundary.reserve(warps * (size_t)(ctx->maxcols + kBoundarySlack) * sizeof(uint2)));
+    SWG_CUDA(ctx, ctx->d_boundary.reserve(2 * warps * (size_t)(ctx->maxcols + kBoundarySlack) * sizeof(uint2)));
     SWG_CUDA(ctx, ctx->d_counters.reserve(std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t)));
     SWG_CUDA(ctx, ctx->d_resc_list.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
     const TopkPlan tp = topk_plan(n_pad, top, nq);
@@ -659,16 +677,46 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                                      ctx->d_profile.as<uint8_t>(), ctx->stream);
             ctx->stats.launches += 1;
         }
-        // long tiles first (they are the critical path), on the 32-thread shape
+        // Long tiles: a sequence is a serial chain of (columns x passes) steps, so a very long one can outlast the
+        // whole rest of the search.  Such tiles go to the 32-thread shape (the shortest step) and start first, on a
+        // few SMs of their own, while the main kernel (launched on the low-priority side stream right behind) fills
+        // the others.  Whether a tile is "long" is decided per query from the estimated run times.
+        uint32_t first_long = ctx->ntiles;
+        if (!same) {
+            if (ctx->long_cols > 0) first_long = ctx->first_long_tile;
+            else {
+                const double total_cycles = (double)m * (double)ctx->local_residues /
+                                            (shape_rate(main_cfg.G, main_cfg.K, main_cfg.passes) * 1e9) * kSmHz;
+                // cycles per column of one warp that shares its scheduler with three others
+                const double step = 4.0 * (16.0 * main_cfg.K + 60.0) * main_cfg.passes;
+                const double limit_cols = 0.35 * total_cycles / step;
+                if ((double)ctx->maxcols > 0.7 * total_cycles / step) {
+                    first_long = (uint32_t)(std::upper_bound(ctx->h_tile_cols.begin(), ctx->h_tile_cols.end(),
+                                                             (uint32_t)std::min(limit_cols, 4.0e9)) - ctx->h_tile_cols.begin());
+                }
+            }
+        }
         uint32_t main_tiles = ctx->ntiles;
-        if (e == cudaSuccess && !same && ctx->first_long_tile < ctx->ntiles) {
-            main_tiles = ctx->first_long_tile;
+        bool forked = false;
+        if (e == cudaSuccess && first_long < ctx->ntiles) {
+            main_tiles = first_long;
+            const uint32_t long_tiles = ctx->ntiles - first_long;
+            const uint64_t long_warps = (uint64_t)long_tiles * kTilePairs;          // one pair per warp at G = 32
+            int long_grid = (int)std::min<uint64_t>((long_warps + warps_per_block - 1) / warps_per_block, kMaxLongBlocks);
+            if (main_tiles == 0) long_grid = grid;                                    // nothing else to run
             p.profile = ctx->d_profile32.as<uint8_t>();
             p.passes = wide_cfg.passes;
-            p.tile_first = ctx->first_long_tile;
-            p.tile_count = ctx->ntiles - ctx->first_long_tile;
+            p.tile_first = first_long;
+            p.tile_count = long_tiles;
             p.task_counter = cnt + 0;
-            e = launch_wavefront(false, wide_cfg, grid, ctx->stream, p);
+            p.boundary = ctx->d_boundary.as<uint2>() + warps * (size_t)p.maxcols;      // its own scratch lines
+            if (main_tiles) {
+                e = cudaEventRecord(ctx->ev_fork, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
+                forked = e == cudaSuccess;
+            }
+            if (e == cudaSuccess) e = launch_wavefront(false, wide_cfg, long_grid, ctx->stream, p);
+            p.boundary = ctx->d_boundary.as<uint2>();
             ctx->stats.launches += 1;
             for (uint32_t t = p.tile_first; t < ctx->ntiles; ++t)
                 padded += (uint64_t)wide_cfg.passes * wide_cfg.G * wide_cfg.K * (ctx->h_tile_cols[t] + wide_cfg.G - 1) * kTileSeqs;
@@ -679,9 +727,11 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             p.tile_first = 0;
             p.tile_count = main_tiles;
             p.task_counter = cnt + 1;
-            e = launch_wavefront(false, main_cfg, grid, ctx->stream, p);
+            e = launch_wavefront(false, main_cfg, grid, forked ? ctx->side_stream : ctx->stream, p);
+            if (e == cudaSuccess && forked) e = cudaEventRecord(ctx->ev_join, ctx->side_stream);
             ctx->stats.launches += 1;
         }
+        if (e == cudaSuccess && forked) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
         if (e == cudaSuccess) {
             p.profile = ctx->d_profile32.as<uint8_t>();
             p.passes = wide_cfg.passes;

@@ -240,11 +240,20 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
             const bool carry_in = MP && pass > 0 && t == 0;
 
             // thread 0 feeds the pipeline: four columns of the pair per trip (two 32-bit words), fetched one trip
-            // ahead, and -- after the first pass -- the (H, F) row parked by the previous pass, one column ahead
+            // ahead, and -- after the first pass -- the (H, F) row parked by the previous pass, four columns ahead
+            // (a ring of four register pairs: an L2 round trip is longer than one column of a short-row shape)
             uint2 w = make_uint2(kPadWord, kPadWord);
             if (t == 0 && data_trips > 0) w = words[0];
-            uint2 hf_next = make_uint2(0u, 0u);
-            if (carry_in) hf_next = __ldcg(bnd);
+            uint2 ring[NC];                   // ring[j] enters the column processed in step j of the current trip
+#pragma unroll
+            for (int j = 0; j < NC; ++j) ring[j] = make_uint2(0u, 0u);
+            if (MP) {
+                ring[0] = hf_in;              // the last column of the previous segment is processed in step 0
+                if (carry_in) {
+#pragma unroll
+                    for (int j = 1; j < NC; ++j) ring[j] = __ldcg(bnd + j - 1);
+                }
+            }
 #pragma unroll 1
             for (uint32_t trip = 0; trip < trips; ++trip) {
                 if (pending && pass == 0 && trip == FI) { finalize(pend_lseq); pending = false; }
@@ -262,11 +271,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
                     const uint32_t word = (j < 2) ? w.x : w.y;
                     uint32_t pkn = prmt(word, 0u, (j & 1) ? selB : selA) | tag;
                     if (j == 0 && trip == 0) pkn |= first_marks;
-                    const uint2 hf = hf_in;           // enters the column processed in this step (column c0 + j - 1)
-                    hf_in = hf_next;                  // enters column c0 + j
+                    const uint2 hf = ring[j];         // (H, F) entering column c0 + j - 1, processed in this step
                     if (MP) {
-                        hf_next = make_uint2(0u, 0u);
-                        if (carry_in && c0 + j + 1 < seg_cols) hf_next = __ldcg(bnd + c0 + j + 1);
+                        ring[j] = make_uint2(0u, 0u);
+                        const uint32_t c = c0 + j + (NC - 1);     // the column processed in step j of the next trip
+                        if (carry_in && c < seg_cols) ring[j] = __ldcg(bnd + c);
                     }
                     column(pkn, hf, sc);
                     if (MP) sc = (sc + 1 == seg_cols) ? 0u : sc + 1;
@@ -274,6 +283,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
                 w = nw;
                 if (MP) __syncwarp();             // orders thread G-1's scratch-line stores before thread 0's later loads
             }
+            if (MP) hf_in = ring[0];          // enters the segment's last column, processed in the next segment's step 0
         }
         if (have) { pending = true; pend_lseq = lseq; }
     }

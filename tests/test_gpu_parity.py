@@ -107,7 +107,8 @@ def test_matrix_and_penalty_sweep(gpu, oracle):
                 assert np.array_equal(got, want), (mat, go, ge)
 
 
-def test_long_sequences_and_32bit_rescore(gpu, oracle):
+@pytest.mark.parametrize("long_threshold", [0, 3072, 64])
+def test_long_sequences_and_32bit_rescore(gpu, oracle, long_threshold):
     """cfg4 in miniature: database sequences above the long-sequence threshold, planted near-copies of a long
     query (score > 32767 -> 32-bit kernel) and partial homologs."""
     rng = np.random.default_rng(77)
@@ -128,7 +129,11 @@ def test_long_sequences_and_32bit_rescore(gpu, oracle):
     want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
     assert want.max() > 32767
     gpu.load_db(dl, dc)
-    got, keys = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 10, want_scores=True)
+    gpu.set_option("long_threshold", long_threshold)     # 0 = per-query estimate; > 0 = fixed column count
+    try:
+        got, keys = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 10, want_scores=True)
+    finally:
+        gpu.set_option("long_threshold", 0)
     assert np.array_equal(got, want), np.argwhere(got != want)[:8]
     assert gpu.stats()["rescored"] > 0
     for qi in range(2):
