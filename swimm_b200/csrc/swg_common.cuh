@@ -32,6 +32,9 @@ constexpr int kMaxRowsPerThread = 32;
 constexpr int kMaxPassRows = 1024;           // 32 threads x 32 rows
 
 constexpr int kBlockThreads = 512;
+// gap penalties with their own kernel instantiations (immediate operands): SWIMM's defaults, -g 10 -e 2
+constexpr int kFastGapOpenExtend = 12;
+constexpr int kFastGapExtend = 2;
 constexpr int kTripCols = 4;                 // database columns per trip of the kernel's column loop
 constexpr int kBoundarySlack = 64;           // scratch-line columns beyond the longest tile (short segments are padded)
 constexpr int kOverflow16 = 32000;           // a 16-bit lane whose best reaches this is redone in 32 bits

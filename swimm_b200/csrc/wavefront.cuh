@@ -38,7 +38,9 @@ constexpr uint32_t kMarkSegment = 1u;   // first column of a segment: the rows r
 constexpr uint32_t kMarkTask = 2u;      // ... and it is the first pass of a new task: the running best is parked
 constexpr uint32_t kMarkCarry = 4u;     // the segment is not the task's last pass: the last row goes to the scratch line
 
-template <class L, int G, int K, bool MP, bool GP>
+// GOE/GE > 0: the gap penalties are compile-time constants and become immediate operands (fewer register-file
+// reads per cell: pipebench mix_v2_immediate_penalties vs mix_v2); 0: taken from the parameter block.
+template <class L, int G, int K, bool MP, bool GP, int GOE, int GE>
 __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfParams p)
 {
     typedef typename L::reg reg;
@@ -72,8 +74,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
     const int g = lane / G;
     const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     uint2 *bnd = p.boundary + (size_t)warp_global * p.maxcols;
-    const reg nge = L::splat(-p.gap_extend);
-    const reg ngoe = L::splat(-p.gap_open_extend);
+    const reg nge = GOE > 0 ? L::splat(-GE) : L::splat(-p.gap_extend);
+    const reg ngoe = GOE > 0 ? L::splat(-GOE) : L::splat(-p.gap_open_extend);
     const uint32_t npass = MP ? p.passes : 1u;
     const uint32_t pad_pk = (L::kSeqs == 2) ? 0x60006000u : 0x00006000u;
     const uint8_t *prof_t = prof + t * 16;
@@ -302,19 +304,19 @@ cudaError_t launch_wf_l32_g32_mp(int K, int grid, size_t smem, cudaStream_t stre
 cudaError_t launch_wf_l16_gp(int grid, cudaStream_t stream, const WfParams &p);
 cudaError_t launch_wf_l32_gp(int grid, cudaStream_t stream, const WfParams &p);
 
-template <class L, int G, int K, bool MP, bool GP>
+template <class L, int G, int K, bool MP, bool GP, int GOE = 0, int GE = 0>
 cudaError_t launch_one(int grid, size_t smem, cudaStream_t stream, const WfParams &p)
 {
     static size_t configured[64] = {0};            // per device: the attribute lives in the device's context
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(wavefront_kernel<L, G, K, MP, GP>,
+        cudaError_t e = cudaFuncSetAttribute(wavefront_kernel<L, G, K, MP, GP, GOE, GE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = smem;
     }
-    wavefront_kernel<L, G, K, MP, GP><<<grid, kBlockThreads, smem, stream>>>(p);
+    wavefront_kernel<L, G, K, MP, GP, GOE, GE><<<grid, kBlockThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
