@@ -259,3 +259,50 @@ def test_cli_search_prints_the_reference_hit_lists(tmp_path, name):
             cur.append([int(m.group(1)), int(m.group(2))])
     assert queries == run["hits"]
     assert "Search speed:" in out and "Execution mode:\t\t\tB200 GPU only (1 GPU" in out
+
+
+def test_full_sort_path_top_larger_than_select_limit(gpu, oracle):
+    """`-r <n>` with n > 2048: the bitonic full sort instead of the selection kernels."""
+    qc, ql, qo, dc, dl, do = _random_case(17, 5000, [64], mu=3.8, sigma=0.5, hi=200, plant=0.02)
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    gpu.load_db(dl, dc)
+    for top in (2049, 5000, 7000):
+        _, keys = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, top)
+        n = min(top, 5000)
+        ts, ti = oracle.top(want[0], n)
+        ks, ki = _keys_to_order(keys[0][:n])
+        assert np.array_equal(ki, ti.astype(np.int64)) and np.array_equal(ks, ts)
+        assert (keys[0][n:] == 0).all()
+
+
+def test_degenerate_inputs(gpu, oracle):
+    b62 = host.submat("blosum62")
+    # a database of one sequence of one residue, a query of one residue
+    gpu.load_db(np.array([1], np.uint16), np.array([5], np.int8))
+    sc, keys = gpu.search(np.array([5], np.int8), np.array([1], np.uint16), np.array([0], np.uint32), b62, 10, 2, 3,
+                          want_scores=True)
+    assert sc.shape == (1, 1) and sc[0, 0] == b62[5, 5]
+    assert keys[0, 0] == (np.uint64(int(b62[5, 5])) << np.uint64(32)) and (keys[0, 1:] == 0).all()
+    # no queries at all
+    sc, keys = gpu.search(np.zeros(0, np.int8), np.zeros(0, np.uint16), np.zeros(0, np.uint32), b62, 10, 2, 3,
+                          want_scores=True)
+    assert sc.shape == (0, 1) and keys.shape == (0, 3)
+    # an empty database
+    gpu.load_db(np.zeros(0, np.uint16), np.zeros(0, np.int8))
+    sc, keys = gpu.search(np.array([5, 6], np.int8), np.array([2], np.uint16), np.array([0], np.uint32), b62, 10, 2, 3,
+                          want_scores=True)
+    assert sc.shape == (1, 0) and (keys == 0).all()
+    # only dummy residues (J/O/U = 23): every score is 0 and the order is index descending
+    gpu.load_db(np.array([3, 3, 4], np.uint16), np.full(10, 23, np.int8))
+    sc, keys = gpu.search(np.full(7, 23, np.int8), np.array([7], np.uint16), np.array([0], np.uint32), b62, 10, 2, 3,
+                          want_scores=True)
+    assert (sc == 0).all() and list(keys[0]) == [2, 1, 0]
+
+
+def test_extreme_penalties_and_zero_gap(gpu, oracle):
+    qc, ql, qo, dc, dl, do = _random_case(23, 200, [40, 120], hi=300)
+    gpu.load_db(dl, dc)
+    for mat, go, ge in [("blosum62", 0, 0), ("blosum62", 0, 1), ("pam30", 127, 127), ("blosum90", 1, 0)]:
+        want = oracle.search(qc, qo, dc, do, host.submat(mat), go, ge)
+        got, _ = gpu.search(qc, ql, qo[:-1], host.submat(mat), go, ge, 0, want_scores=True)
+        assert np.array_equal(got, want), (mat, go, ge)
