@@ -28,9 +28,15 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner (printed to stdout under NCCL_DEBUG=VERSION) out of it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line.  Libraries (NCCL's version banner, for one) print to file descriptor 1
+# behind Python's back, so fd 1 is pointed at stderr for the whole run and the line is written to the saved fd.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 
 from swimm_b200 import host, synth  # noqa: E402
 
@@ -352,7 +358,7 @@ def main():
                                            for i in range(q.n) if q_secs[i] > 0}}}
     if world > 1:
         dist.destroy_process_group()
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -392,7 +398,7 @@ def bench_reference(args, cores):
                              "sample": what + ("; swimm -S search -m 0 -v 32 -c %d (printed Search time)" % cores
                                                if kind == "reference" else "; scalar oracle port, OpenMP")},
             "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
