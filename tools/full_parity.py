@@ -1,0 +1,72 @@
+"""cfg2 at full size through BOTH command lines on the GPU box: the unmodified reference
+(oracle/_ref/swimm -S search -m 0 -v 32 -c <cores>) and this repo's swimm (-m 3).  Compares the printed hit
+lists and reports both search times.  Usage: python tools/full_parity.py [scale] [top] [gpus]"""
+import os, re, subprocess, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from swimm_b200 import synth
+
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+top = sys.argv[2] if len(sys.argv) > 2 else "10"
+gpus = sys.argv[3] if len(sys.argv) > 3 else "1"
+REF = os.path.join(ROOT, "oracle", "_ref", "swimm")
+OURS = os.path.join(ROOT, "swimm_b200", "swimm")
+cores = str(os.cpu_count() or 4)
+
+
+def hits(stdout):
+    out, cur = [], None
+    for line in stdout.split("\n"):
+        if line.startswith("Query description:"):
+            cur = []
+            out.append(cur)
+        m = re.match(r"^(-?\d+)\t(.*)$", line)
+        if m and cur is not None:
+            cur.append((int(m.group(1)), re.sub(r"[^\x20-\x7e]", "", m.group(2)).strip()))
+    return out
+
+
+def field(stdout, name):
+    for line in stdout.split("\n"):
+        if line.startswith(name):
+            return line.split("\t")[-1].strip()
+    return "?"
+
+
+q = synth.make_queries(np.random.default_rng(7), synth.QUERY_LENGTHS)
+db = synth.make_db(1000, int(570_000 * scale) // 16 * 16, mu=5.675, queries=q)
+with tempfile.TemporaryDirectory() as tmp:
+    dbf, qf = os.path.join(tmp, "db.fasta"), os.path.join(tmp, "q.fasta")
+    t0 = time.time()
+    synth.write_fasta(dbf, db, width=900)
+    synth.write_fasta(qf, q)
+    print("FASTA written: %d sequences, %d residues (%.1f s)" % (db.n, int(db.lengths.sum()), time.time() - t0))
+    t0 = time.time()
+    subprocess.run([REF, "-S", "preprocess", "-i", dbf, "-o", os.path.join(tmp, "ref"), "-c", cores], check=True, stdout=subprocess.DEVNULL)
+    t_ref_pre = time.time() - t0
+    t0 = time.time()
+    subprocess.run([OURS, "-S", "preprocess", "-i", dbf, "-o", os.path.join(tmp, "ours")], check=True, stdout=subprocess.DEVNULL)
+    t_our_pre = time.time() - t0
+    same_files = all(open(os.path.join(tmp, "ref." + e), "rb").read() == open(os.path.join(tmp, "ours." + e), "rb").read()
+                     for e in ("info", "seq", "desc"))
+    print("preprocess: reference %.1f s, this repo %.1f s, files identical: %s" % (t_ref_pre, t_our_pre, same_files))
+    t0 = time.time()
+    ref = subprocess.run([REF, "-S", "search", "-q", qf, "-d", os.path.join(tmp, "ref"), "-m", "0", "-v", "32", "-c", cores, "-r", top],
+                         check=True, capture_output=True).stdout.decode("latin-1")
+    t_ref = time.time() - t0
+    t0 = time.time()
+    ours = subprocess.run([OURS, "-S", "search", "-q", qf, "-d", os.path.join(tmp, "ours"), "-m", "3", "-x", gpus, "-r", top],
+                          check=True, capture_output=True).stdout.decode("latin-1")
+    t_ours = time.time() - t0
+h_ref, h_ours = hits(ref), hits(ours)
+ok = h_ref == h_ours and len(h_ref) == q.n
+print("reference: Search time %s, %s, wall %.1f s (%s threads)" % (field(ref, "Search time:"), field(ref, "Search speed:"), t_ref, cores))
+print("this repo: Search time %s, %s, wall %.1f s (%s)" % (field(ours, "Search time:"), field(ours, "Search speed:"), t_ours, field(ours, "Execution mode:")))
+print("hit lists identical for %d queries x top %s: %s" % (len(h_ref), top, ok))
+if not ok:
+    for i, (a, b) in enumerate(zip(h_ref, h_ours)):
+        if a != b:
+            print("first difference in query", i + 1, [x for x in zip(a, b) if x[0] != x[1]][:3])
+            break
+sys.exit(0 if ok else 1)
