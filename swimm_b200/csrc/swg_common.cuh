@@ -31,7 +31,10 @@ constexpr int kPassBytes = kLetters * kLetterStride;
 constexpr int kMaxRowsPerThread = 32;
 constexpr int kMaxPassRows = 1024;           // 32 threads x 32 rows
 
-constexpr int kBlockThreads = 512;
+#ifndef SWG_BLOCK_THREADS
+#define SWG_BLOCK_THREADS 512
+#endif
+constexpr int kBlockThreads = SWG_BLOCK_THREADS;
 // gap penalties with their own kernel instantiations (immediate operands): SWIMM's defaults, -g 10 -e 2
 constexpr int kFastGapOpenExtend = 12;
 constexpr int kFastGapExtend = 2;
