@@ -25,6 +25,8 @@
 // the reference's 8 -> 16 -> 32 bit escalation (CPUsearch.c:678-956).
 #pragma once
 
+#include <type_traits>
+
 #include "swg_common.cuh"
 
 namespace swg {
@@ -78,7 +80,6 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
     const reg ngoe = GOE > 0 ? L::splat(-GOE) : L::splat(-p.gap_open_extend);
     const uint32_t npass = MP ? p.passes : 1u;
     const uint32_t pad_pk = (L::kSeqs == 2) ? 0x60006000u : 0x00006000u;
-    const uint8_t *prof_t = prof + t * 16;
 
     uint32_t ntasks;
     if (L::kSeqs == 2) ntasks = p.tile_count * TPT;
@@ -103,7 +104,15 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
 
     // One step of this thread: process the column whose word arrived in the previous step, using (H, F) of the
     // row above handed down now, and prepare DS for the column whose word arrives now.
-    auto column = [&](uint32_t in_pkn, uint2 in_hf, uint32_t store_col) {
+    //
+    // Two versions.  HEAD (the first G steps of a segment): threads may still be in the previous segment, so the
+    // marks of every column word are looked at -- restart of the rows, profile slice of the word's pass, whether
+    // the last row is carried.  Steady state (all later steps): every thread is inside the current segment, nothing
+    // of that is looked at, the profile slice and the carry decision are per-segment values.
+    uint32_t slice_off = (uint32_t)t * 16;     // byte offset of this thread's rows in the current pass's profile slice
+    bool store_on = false;                     // steady state: this thread parks its last row (thread G-1, carried pass)
+    auto column = [&](auto head_tag, uint32_t in_pkn, uint2 in_hf, uint32_t store_col) {
+        constexpr bool HEAD = decltype(head_tag)::value;
         uint32_t pkn = __shfl_up_sync(0xffffffffu, pk, 1, G);
         reg r_h = (reg)__shfl_up_sync(0xffffffffu, out_h, 1, G);
         reg r_f = (reg)__shfl_up_sync(0xffffffffu, out_f, 1, G);
@@ -119,15 +128,18 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
         uint32_t w1[KCH * 4], w2[KCH * 4];
         {
             const uint32_t hi = pkn >> 16;
-            const uint8_t *pb = MP ? prof_t + (hi & 0xffu) * kPassBytes : prof_t;
-            const uint4 *q1 = reinterpret_cast<const uint4 *>(pb + (pkn & 0xff00u));
+            if (MP && HEAD) slice_off = (uint32_t)t * 16 + (hi & 0xffu) * kPassBytes;
+            // letter offset (bits 10..14) and thread offset (bits 4..8) do not overlap: one logic op when there is one slice
+            const uint32_t oa = MP ? slice_off + (pkn & 0xff00u) : ((pkn & 0xff00u) | slice_off);
+            const uint32_t ob = MP ? slice_off + (hi & 0xff00u) : ((hi & 0xff00u) | slice_off);
+            const uint4 *q1 = reinterpret_cast<const uint4 *>(prof + oa);
 #pragma unroll
             for (int i = 0; i < KCH; ++i) {
                 const uint4 v = q1[i * G];
                 w1[4 * i] = v.x; w1[4 * i + 1] = v.y; w1[4 * i + 2] = v.z; w1[4 * i + 3] = v.w;
             }
             if (L::kSeqs == 2) {
-                const uint4 *q2 = reinterpret_cast<const uint4 *>(pb + (hi & 0xff00u));
+                const uint4 *q2 = reinterpret_cast<const uint4 *>(prof + ob);
 #pragma unroll
                 for (int i = 0; i < KCH; ++i) {
                     const uint4 v = q2[i * G];
@@ -167,14 +179,16 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
         }
         out_h = hp;
         out_f = f;
-        if (MP && t == G - 1 && (pk_cur & kMarkCarry))
+        if (MP && (HEAD ? (t == G - 1 && (pk_cur & kMarkCarry)) : store_on))
             bnd[store_col] = make_uint2((uint32_t)out_h, (uint32_t)out_f);
-        if (pkn & kMarkSegment) {          // rare and divergent: the next column starts a segment
+        if (HEAD && (pkn & kMarkSegment)) {          // rare and divergent: the next column starts a segment
 #pragma unroll
             for (int x = 0; x < K; ++x) { DS[x] = score_of(x); E[x] = L::splat(0); }
             if (pkn & kMarkTask) { bsave = best; best = L::splat(0); }
         }
     };
+    const std::true_type head_steps;
+    const std::false_type steady_steps;
 
     // Store the scores of a task whose last column has left the pipeline (all threads hold its best in bsave).
     auto finalize = [&](uint32_t lseq) {
@@ -256,35 +270,38 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
                     for (int j = 1; j < NC; ++j) ring[j] = __ldcg(bnd + j - 1);
                 }
             }
-#pragma unroll 1
-            for (uint32_t trip = 0; trip < trips; ++trip) {
-                if (pending && pass == 0 && trip == FI) { finalize(pend_lseq); pending = false; }
+            // One trip = four steps.  The words of columns 4*trip .. 4*trip+3 enter; the cells processed are those of
+            // columns 4*trip-1 .. 4*trip+2.  Thread G-1 runs G-1 columns behind thread 0: during the head trips its
+            // scratch-line column may still lie in the previous pass (same task, same length).
+            auto trip_body = [&](auto head_tag, uint32_t trip) {
                 uint2 nw = make_uint2(kPadWord, kPadWord);
                 const uint32_t nt = trip + 1;
                 if (t == 0 && nt < data_trips) nw = words[(nt >> 1) * (kTilePairs * 2) + (nt & 1u)];
-                // The words of columns 4*trip .. 4*trip+3 enter now; the cells processed in these four steps are
-                // those of columns 4*trip-1 .. 4*trip+2.  Thread G-1 runs G-1 columns behind thread 0: its
-                // scratch-line column may still lie in the previous pass (same task, same length).
                 const uint32_t c0 = trip * NC;
                 uint32_t sc = c0 + seg_cols - G;
-                if (sc >= seg_cols) sc -= seg_cols;
+                if (sc >= seg_cols) sc -= seg_cols;         // a multiple of 4: the four columns of a trip never wrap
 #pragma unroll
                 for (int j = 0; j < NC; ++j) {
                     const uint32_t word = (j < 2) ? w.x : w.y;
                     uint32_t pkn = prmt(word, 0u, (j & 1) ? selB : selA) | tag;
-                    if (j == 0 && trip == 0) pkn |= first_marks;
+                    if (decltype(head_tag)::value && j == 0 && trip == 0) pkn |= first_marks;
                     const uint2 hf = ring[j];         // (H, F) entering column c0 + j - 1, processed in this step
                     if (MP) {
                         ring[j] = make_uint2(0u, 0u);
                         const uint32_t c = c0 + j + (NC - 1);     // the column processed in step j of the next trip
                         if (carry_in && c < seg_cols) ring[j] = __ldcg(bnd + c);
                     }
-                    column(pkn, hf, sc);
-                    if (MP) sc = (sc + 1 == seg_cols) ? 0u : sc + 1;
+                    column(head_tag, pkn, hf, sc + j);
                 }
                 w = nw;
                 if (MP) __syncwarp();             // orders thread G-1's scratch-line stores before thread 0's later loads
-            }
+            };
+#pragma unroll 1
+            for (uint32_t trip = 0; trip < FI; ++trip) trip_body(head_steps, trip);
+            if (pending && pass == 0) { finalize(pend_lseq); pending = false; }
+            store_on = MP && t == G - 1 && (pass + 1 < seg_passes);
+#pragma unroll 1
+            for (uint32_t trip = FI; trip < trips; ++trip) trip_body(steady_steps, trip);
             if (MP) hf_in = ring[0];          // enters the segment's last column, processed in the next segment's step 0
         }
         if (have) { pending = true; pend_lseq = lseq; }
