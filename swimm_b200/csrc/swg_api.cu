@@ -20,7 +20,7 @@ using namespace swg;
 
 namespace {
 
-constexpr int kMaxSmemPasses = 8;            // 8 x 25 KB of query profile per CTA
+constexpr int kMaxSmemPasses = 7;            // 7 x 32 KB profile slices per CTA
 constexpr uint32_t kDefaultLongCols = 3072;
 constexpr uint64_t kMaxLongBlocks = 12;
 constexpr double kSmHz = 1.9e9;              // SM clock assumed by the long-tile estimate      // SMs the long-tile launch may take while the main kernel runs  // tiles with more columns than this go to the 32-thread kernel

@@ -27,7 +27,9 @@ constexpr uint32_t kPadWord = 0x60606060u;   // four pad residues (24*4)
 // -> 8 distinct 16-byte bank groups, conflict-free for G >= 8 whatever letters the threads look up.
 constexpr int kLetters = 25;
 constexpr int kLetterStride = 1024;
-constexpr int kPassBytes = kLetters * kLetterStride;
+constexpr int kPassBytes = 32768;             // slice of one pass: 25 letter rows, padded to a power of two so that
+                                             // pass, letter and thread offsets occupy disjoint address bits
+static_assert(kLetters * kLetterStride <= kPassBytes, "profile slice");
 constexpr int kMaxRowsPerThread = 32;
 constexpr int kMaxPassRows = 1024;           // 32 threads x 32 rows
 

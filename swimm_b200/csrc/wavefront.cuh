@@ -34,7 +34,7 @@ namespace swg {
 // A column travels down the pipeline as one 32-bit word:
 //   bits 15:8  = 4 * residue code of sequence A  (so that word & 0xff00 is the profile offset code * 1024)
 //   bits 31:24 = 4 * residue code of sequence B
-//   bits 23:16 = pass of the segment the column belongs to (selects the 25 KB profile slice)
+//   bits 23:16 = pass of the segment the column belongs to (selects the 32 KB profile slice)
 //   bits  2:0  = marks
 constexpr uint32_t kMarkSegment = 1u;   // first column of a segment: the rows restart from H = E = 0
 constexpr uint32_t kMarkTask = 2u;      // ... and it is the first pass of a new task: the running best is parked
@@ -129,9 +129,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
         {
             const uint32_t hi = pkn >> 16;
             if (MP && HEAD) slice_off = (uint32_t)t * 16 + (hi & 0xffu) * kPassBytes;
-            // letter offset (bits 10..14) and thread offset (bits 4..8) do not overlap: one logic op when there is one slice
-            const uint32_t oa = MP ? slice_off + (pkn & 0xff00u) : ((pkn & 0xff00u) | slice_off);
-            const uint32_t ob = MP ? slice_off + (hi & 0xff00u) : ((hi & 0xff00u) | slice_off);
+            // pass (bits 15..), letter (bits 10..14) and thread (bits 4..9) offsets do not overlap: one logic op each
+            const uint32_t oa = (pkn & 0xff00u) | slice_off;
+            const uint32_t ob = (hi & 0xff00u) | slice_off;
             const uint4 *q1 = reinterpret_cast<const uint4 *>(prof + oa);
 #pragma unroll
             for (int i = 0; i < KCH; ++i) {
@@ -245,15 +245,16 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
         const uint32_t data_trips = ncols / NC;
         const uint32_t trips = data_trips < kMinTrips ? kMinTrips : data_trips;
         const uint32_t seg_cols = trips * NC;
-        // PRMT selectors that turn a residue byte (code*4) into byte lanes 1 and 3 of the column word
-        const uint32_t selA = (L::kSeqs == 2) ? 0x1404u : (0x4404u | (half << 4));
-        const uint32_t selB = (L::kSeqs == 2) ? 0x3424u : (0x4404u | ((2u + half) << 4));
+        // PRMT selectors that build a column word: residue bytes (code*4) of the pair go to byte lanes 1 and 3, byte
+        // lanes 0 and 2 (marks, pass) are taken from the second operand -- tagging costs no instruction
+        const uint32_t selA = (L::kSeqs == 2) ? 0x1604u : (0x7604u | (half << 4));
+        const uint32_t selB = (L::kSeqs == 2) ? 0x3624u : (0x7604u | ((2u + half) << 4));
         const uint32_t seg_passes = have ? npass : 1u;
 
         for (uint32_t pass = 0; pass < seg_passes; ++pass) {
             const uint32_t first_marks = kMarkSegment | (pass == 0 ? kMarkTask : 0u);
             const uint32_t tag = MP ? ((pass << 16) | ((pass + 1 < seg_passes) ? kMarkCarry : 0u)) : 0u;
-            const bool carry_in = MP && pass > 0 && t == 0;
+            const bool carry_in = MP && pass > 0;
 
             // thread 0 feeds the pipeline: four columns of the pair per trip (two 32-bit words), fetched one trip
             // ahead, and -- after the first pass -- the (H, F) row parked by the previous pass, four columns ahead
@@ -283,14 +284,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
 #pragma unroll
                 for (int j = 0; j < NC; ++j) {
                     const uint32_t word = (j < 2) ? w.x : w.y;
-                    uint32_t pkn = prmt(word, 0u, (j & 1) ? selB : selA) | tag;
-                    if (decltype(head_tag)::value && j == 0 && trip == 0) pkn |= first_marks;
+                    const bool first = decltype(head_tag)::value && j == 0 && trip == 0;
+                    const uint32_t pkn = prmt(word, first ? (tag | first_marks) : tag, (j & 1) ? selB : selA);
                     const uint2 hf = ring[j];         // (H, F) entering column c0 + j - 1, processed in this step
-                    if (MP) {
-                        ring[j] = make_uint2(0u, 0u);
-                        const uint32_t c = c0 + j + (NC - 1);     // the column processed in step j of the next trip
-                        if (carry_in && c < seg_cols) ring[j] = __ldcg(bnd + c);
-                    }
+                    // the column processed in step j of the next trip (the line has slack past the segment's end:
+                    // entries read there are never used); pass 0 keeps the zeros the ring was initialised with
+                    if (MP && pass > 0) ring[j] = __ldcg(bnd + c0 + j + (NC - 1));
                     column(head_tag, pkn, hf, sc + j);
                 }
                 w = nw;
