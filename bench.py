@@ -318,8 +318,19 @@ def main():
             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
         db_bytes = st["db_bytes"]
         algo_gbs = db_bytes * q.n * args.steps / search_s / 1e9     # every query streams the tiled database once
+        # DRAM traffic of one search launch from the committed ncu --set full capture (bytes read + written)
+        traffic = None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_cfg2_three_kernels.json")))["q144"]
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = sum(float(cap[k].split()[0]) * unit[cap[k].split()[1]]
+                          for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        except Exception:
+            pass
         roof = {"bound": "int_alu", "achieved": search_gcups, "peak": peak_gcups, "unit": "GCUPS",
-                "frac": search_gcups / peak_gcups, "traffic": None,
+                "frac": search_gcups / peak_gcups, "traffic": traffic,
+                "traffic_note": "ncu dram bytes read+written by one full-size search launch (profiles/r01_ncu_full_cfg2_three_"
+                                "kernels.json, q144); algorithmic bytes per launch = the tiled database, %d" % db_bytes,
                 "kernel": "wavefront_kernel<Lane16,G,K> (all 16-bit search launches of a step)",
                 "mix": "6.5 integer instr per 2 cells: 4.5 on the ALU pipe (PRMT, VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + "
                        "2 VIADD.16x2 (gap penalties as immediates); measured %.1f thread-instr/clk/SM at %.0f MHz"
