@@ -10,6 +10,7 @@ from swimm_b200 import synth
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 top = sys.argv[2] if len(sys.argv) > 2 else "10"
 gpus = sys.argv[3] if len(sys.argv) > 3 else "1"
+workload = sys.argv[4] if len(sys.argv) > 4 else "cfg2"
 REF = os.path.join(ROOT, "oracle", "_ref", "swimm")
 OURS = os.path.join(ROOT, "swimm_b200", "swimm")
 cores = str(os.cpu_count() or 4)
@@ -34,8 +35,24 @@ def field(stdout, name):
     return "?"
 
 
-q = synth.make_queries(np.random.default_rng(7), synth.QUERY_LENGTHS)
-db = synth.make_db(1000, int(570_000 * scale) // 16 * 16, mu=5.675, queries=q)
+if workload == "cfg2":
+    q = synth.make_queries(np.random.default_rng(7), synth.QUERY_LENGTHS)
+    db = synth.make_db(1000, int(570_000 * scale) // 16 * 16, mu=5.675, queries=q)
+elif workload == "cfg4":
+    # long-sequence stress: every database sequence longer than 3000 residues (up to the format's 65535), planted
+    # near-copies of a long query (scores beyond 16 bits -> 32-bit kernel) and partial homologs
+    rng = np.random.default_rng(44)
+    q = synth.make_queries(rng, [144, 1000, 3100, 5478])
+    n = int(8000 * scale)
+    lens = np.concatenate([rng.integers(3001, 20000, n - 8), [30000, 40000, 50000, 60000, 65535, 65535, 3001, 3002]])
+    db = synth.make_seqset(rng, lens)
+    synth.plant(rng, db, q, fraction=0.02, frag_range=(50, 3000), rate=0.1)
+    for t, qi, rate in [(5, 3, 0.0), (6, 3, 0.01), (7, 2, 0.0), (n - 3, 3, 0.0)]:
+        s0 = db.offsets[t]
+        L = len(q.seq(qi))
+        db.residues[s0 + 11:s0 + 11 + L] = synth.mutate(rng, q.seq(qi), rate)
+else:
+    raise SystemExit("unknown workload " + workload)
 with tempfile.TemporaryDirectory() as tmp:
     dbf, qf = os.path.join(tmp, "db.fasta"), os.path.join(tmp, "q.fasta")
     t0 = time.time()
