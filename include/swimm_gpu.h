@@ -115,7 +115,9 @@ int swg_gpu_pipebench(swg_ctx *ctx, int max_probes, double *ginstr_per_s, double
  * "profile32", "scores", "counters"}; *bytes receives the buffer's size, at most max_bytes are copied. */
 int swg_gpu_debug_read(swg_ctx *ctx, const char *name, void *out, uint64_t max_bytes, uint64_t *bytes);
 
-/* tuning knobs (all optional): name in {"long_threshold", "force_group", "force_rows", "block_threads"} */
+/* tuning knobs (all optional): name in {"long_threshold", "force_group", "force_rows", "block_threads",
+ * "query_pairing" (0 never / 1 planner / 2 always pair the queries of a batch for the query-pair kernel),
+ * "q2_group", "q2_rows" (forced shape of the query-pair kernel), "grid_blocks" (CTAs per search launch, 0 = one per SM)} */
 int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value);
 
 /* Drop-in with the reference signature (CPUsearch.h:37-39).  n_threads is read as the number of GPUs

@@ -15,6 +15,7 @@
 #include "../../include/swimm_gpu.h"
 #include "swg_internal.h"
 #include "wavefront.cuh"
+#include "wavefront_q2.cuh"
 
 using namespace swg;
 
@@ -29,6 +30,18 @@ struct Config {          // how one query is mapped onto thread groups
     int G, K;
     uint32_t passes;
     bool global_profile;
+};
+
+struct PairConfig {      // how a query pair is mapped onto the query-pair kernel (wavefront_q2.cuh)
+    int G, K;
+    uint32_t passes;
+    double cost;         // estimated run time per database residue (arbitrary units shared with the single-query planner)
+};
+
+struct WorkItem {        // one entry of a batch's schedule: a single query, or a pair searched by the query-pair kernel
+    uint32_t qa, qb;     // query indices (qb unused for a single query)
+    bool pair;
+    PairConfig pc;
 };
 
 struct DeviceBuf {
@@ -74,7 +87,8 @@ struct swg_ctx {
     uint32_t maxcols = 8;
     double avg_cols = 8;
     std::vector<uint32_t> h_tile_cols;
-    DeviceBuf d_db, d_tile_off, d_tile_cols;
+    DeviceBuf d_db, d_tile_off, d_tile_cols, d_line_off;
+    uint64_t line_units = 0;         // uint2 entries of all per-sequence pass lines (query-pair kernel, multi-pass)
 
     // queries of the current batch
     bool queries_ready = false;
@@ -86,6 +100,9 @@ struct swg_ctx {
 
     // work buffers
     DeviceBuf d_scores, d_profile, d_profile32, d_boundary, d_counters, d_resc_list, d_topk_scratch, d_top_out;
+    DeviceBuf d_profile_q2, d_lines, d_resc_list2, d_q2_counters;
+    std::vector<WorkItem> items;            // schedule of the last run
+    std::vector<cudaEvent_t> item_events;   // items.size() + 1 marks
     std::vector<uint32_t> h_counters;
     std::vector<cudaEvent_t> q_events;      // q_count + 1 marks around every query's kernels
     std::vector<double> q_seconds;
@@ -95,6 +112,9 @@ struct swg_ctx {
     // options
     long long_cols = kDefaultLongCols;
     long force_group = 0, force_rows = 0;
+    long query_pairing = 1;                 // 0: never pair queries, 1: pair when the planner expects a gain, 2: always
+    long q2_group = 0, q2_rows = 0;         // forced shape of the query-pair kernel (0: planner)
+    long grid_blocks = 0;                   // CTAs per search launch (0: one per SM); small values make every warp run many tasks
 
     swg_stats stats;
 };
@@ -185,6 +205,43 @@ Config choose_config(uint32_t m, double avg_cols, long force_group, long force_r
     return best;
 }
 
+// Shape of the query-pair kernel for a pair whose longer query has m rows: G in {8, 16, 32}, K in {8, 12, ..., 32},
+// passes = ceil(m / (G*K)); minimises passes * rows / rate like choose_config.
+double q2_rate(int G, int K, uint32_t passes)
+{
+    const float *tab = passes > 1 ? kRateQ2Multi_G32 : G == 8 ? kRateQ2_G8 : G == 16 ? kRateQ2_G16 : kRateQ2_G32;
+    return tab[K / 4];
+}
+
+PairConfig choose_pair_config(uint32_t m, long force_group, long force_rows)
+{
+    PairConfig best = {32, 32, (m + 1023) / 1024, 1e300};
+    if (m == 0) m = 1;
+    for (int G = 8; G <= 32; G *= 2) {
+        if (force_group && G != force_group) continue;
+        for (int K = 8; K <= kMaxRowsPerThread; K += 4) {
+            if (force_rows && K != force_rows) continue;
+            const uint32_t rows = (uint32_t)(G * K);
+            const uint32_t passes = (m + rows - 1) / rows;
+            if (passes > 1 && G != 32 && !force_group) continue;      // fewer, longer passes: less line traffic
+            // the rate tables count the cells of BOTH queries: cost per database residue = rows * passes / (rate / 2)
+            const double c = 2.0 * passes * rows / q2_rate(G, K, passes);
+            if (c < best.cost) best = {G, K, passes, c};
+        }
+    }
+    return best;
+}
+
+cudaError_t launch_q2(const PairConfig &pc, bool cin, bool cout, int grid, cudaStream_t stream, const WfParams &p)
+{
+    switch (pc.G) {
+        case 8: return launch_q2_g8(pc.K, cin, cout, grid, stream, p);
+        case 16: return launch_q2_g16(pc.K, cin, cout, grid, stream, p);
+        case 32: return launch_q2_g32(pc.K, cin, cout, grid, stream, p);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 // the 32-thread shape used for long tiles and for the 32-bit re-computation
 Config wide_config(uint32_t m)
 {
@@ -223,6 +280,8 @@ void free_db(swg_ctx *c)
     c->d_db.release();
     c->d_tile_off.release();
     c->d_tile_cols.release();
+    c->d_line_off.release();
+    c->d_lines.release();
     c->db_ready = false;
 }
 
@@ -231,7 +290,7 @@ void free_db(swg_ctx *c)
 int finish_load(swg_ctx *ctx, const std::vector<uint16_t> &len, const std::vector<uint64_t> &off, const int8_t *d_res)
 {
     const uint32_t ntiles = (uint32_t)(len.size() / kTileSeqs);
-    std::vector<uint64_t> tile_off(ntiles + 1, 0);
+    std::vector<uint64_t> tile_off(ntiles + 1, 0), line_off(ntiles + 1, 0);
     ctx->h_tile_cols.assign(ntiles, 0);
     uint32_t maxcols = kChunkCols;
     double sum_cols = 0;
@@ -241,6 +300,8 @@ int finish_load(swg_ctx *ctx, const std::vector<uint16_t> &len, const std::vecto
         const uint32_t cols = (mx + kChunkCols - 1) / kChunkCols * kChunkCols;
         ctx->h_tile_cols[t] = cols;
         tile_off[t + 1] = tile_off[t] + (uint64_t)(cols / kChunkCols) * kTilePairs;
+        // pass lines of the query-pair kernel: 16 per tile, each max(cols, kQ2MinSegCols) + kQ2LineSlack entries
+        line_off[t + 1] = line_off[t] + (uint64_t)kTileSeqs * (std::max<uint32_t>(cols, kQ2MinSegCols) + kQ2LineSlack);
         maxcols = std::max(maxcols, cols);
         sum_cols += cols;
     }
@@ -248,6 +309,7 @@ int finish_load(swg_ctx *ctx, const std::vector<uint16_t> &len, const std::vecto
     ctx->maxcols = maxcols;
     ctx->avg_cols = ntiles ? sum_cols / ntiles : 8.0;
     ctx->db_units = tile_off[ntiles];
+    ctx->line_units = line_off[ntiles];
     uint32_t fl = ntiles;
     while (fl > 0 && ctx->h_tile_cols[fl - 1] > (uint32_t)ctx->long_cols) --fl;   // lengths ascend: long tiles are last
     ctx->first_long_tile = fl;
@@ -256,10 +318,14 @@ int finish_load(swg_ctx *ctx, const std::vector<uint16_t> &len, const std::vecto
     SWG_CUDA(ctx, ctx->d_db.reserve(std::max<uint64_t>(ctx->db_units, 1) * sizeof(uint4)));
     SWG_CUDA(ctx, ctx->d_tile_off.reserve((ntiles + 1) * sizeof(uint64_t)));
     SWG_CUDA(ctx, ctx->d_tile_cols.reserve(std::max<uint32_t>(ntiles, 1) * sizeof(uint32_t)));
+    SWG_CUDA(ctx, ctx->d_line_off.reserve((ntiles + 1) * sizeof(uint64_t)));
     SWG_CUDA(ctx, d_off.reserve(off.size() * sizeof(uint64_t)));
     SWG_CUDA(ctx, d_len.reserve(std::max<size_t>(len.size(), 1) * sizeof(uint16_t)));
     cudaError_t e = cudaMemcpyAsync(ctx->d_tile_off.p, tile_off.data(), (ntiles + 1) * sizeof(uint64_t),
                                     cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ctx->d_line_off.p, line_off.data(), (ntiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                            ctx->stream);
     if (e == cudaSuccess && ntiles)
         e = cudaMemcpyAsync(ctx->d_tile_cols.p, ctx->h_tile_cols.data(), ntiles * sizeof(uint32_t), cudaMemcpyHostToDevice,
                             ctx->stream);
@@ -352,7 +418,11 @@ void swg_gpu_destroy(swg_ctx *ctx)
     ctx->d_resc_list.release();
     ctx->d_topk_scratch.release();
     ctx->d_top_out.release();
+    ctx->d_profile_q2.release();
+    ctx->d_resc_list2.release();
+    ctx->d_q2_counters.release();
     for (cudaEvent_t ev : ctx->q_events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->item_events) cudaEventDestroy(ev);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_search_end) cudaEventDestroy(ctx->ev_search_end);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
@@ -383,6 +453,19 @@ int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value)
     } else if (!strcmp(name, "force_rows")) {
         if (value < 0 || value > kMaxRowsPerThread) return fail(ctx, SWG_ERR_ARG, "force_rows must be 0..32");
         ctx->force_rows = value;
+    } else if (!strcmp(name, "query_pairing")) {
+        if (value < 0 || value > 2) return fail(ctx, SWG_ERR_ARG, "query_pairing must be 0 (off), 1 (planner) or 2 (always)");
+        ctx->query_pairing = value;
+    } else if (!strcmp(name, "q2_group")) {
+        if (value != 0 && value != 8 && value != 16 && value != 32) return fail(ctx, SWG_ERR_ARG, "q2_group must be 0, 8, 16 or 32");
+        ctx->q2_group = value;
+    } else if (!strcmp(name, "q2_rows")) {
+        if (value < 0 || value > kMaxRowsPerThread || value % 4 || value == 4)
+            return fail(ctx, SWG_ERR_ARG, "q2_rows must be 0 or a multiple of 4 in 8..32");
+        ctx->q2_rows = value;
+    } else if (!strcmp(name, "grid_blocks")) {
+        if (value < 0) return fail(ctx, SWG_ERR_ARG, "grid_blocks must be >= 0");
+        ctx->grid_blocks = value;
     } else if (!strcmp(name, "block_threads")) {
         if (value != kBlockThreads) return fail(ctx, SWG_ERR_ARG, "block_threads is fixed at %d in this build", kBlockThreads);
     } else {
@@ -613,7 +696,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     ctx->stats.padded_cells = 0;
     ctx->stats.rescored = 0;
 
-    const int grid = ctx->sm_count;
+    const int grid = ctx->grid_blocks > 0 ? (int)std::min<long>(ctx->grid_blocks, ctx->sm_count) : ctx->sm_count;
     const int warps_per_block = kBlockThreads / 32;
     const size_t warps = (size_t)grid * warps_per_block;
     std::vector<Config> main_cfgs(nq), wide_cfgs(nq);
@@ -623,18 +706,74 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         wide_cfgs[q] = wide_config(ctx->q_len[q]);
         max_passes = std::max(max_passes, std::max(main_cfgs[q].passes, wide_cfgs[q].passes));
     }
+
+    // ---- schedule: queries of similar length are paired and searched by the query-pair kernel when the planner
+    // expects that to be faster than two runs of the sequence-pair kernel; the others run one by one ----
+    std::vector<WorkItem> &items = ctx->items;
+    items.clear();
+    uint32_t q2_launches = 0, q2_max_passes = 0;
+    bool q2_lines = false;
+    {
+        std::vector<uint32_t> order(nq);
+        for (uint64_t q = 0; q < nq; ++q) order[q] = (uint32_t)q;
+        std::vector<char> paired(nq, 0);
+        if (ctx->query_pairing && nq >= 2 && ctx->ntiles) {
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return ctx->q_len[x] > ctx->q_len[y]; });
+            for (uint64_t i = 0; i + 1 < nq; i += 2) {
+                const uint32_t qa = order[i + 1], qb = order[i];          // qb is the longer one
+                const uint32_t m = ctx->q_len[qb];
+                const PairConfig pc = choose_pair_config(m, ctx->q2_group, ctx->q2_rows);
+                bool use = ctx->query_pairing == 2;
+                if (!use) {
+                    double single = 0;
+                    for (uint32_t q : {qa, qb}) {
+                        const Config &c = main_cfgs[q];
+                        single += (double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes);
+                    }
+                    // a sequence is a serial chain of columns: the longest one must not outlast the rest of a launch
+                    const double launch_cycles = (double)pc.G * pc.K * (double)ctx->local_residues /
+                                                 (q2_rate(pc.G, pc.K, pc.passes) * 0.5e9) * kSmHz;
+                    const double step = 4.0 * (12.0 * pc.K + 60.0);
+                    use = pc.cost < single && (double)ctx->maxcols * step < 0.5 * launch_cycles;
+                }
+                if (!use) continue;
+                WorkItem it;
+                it.qa = qa; it.qb = qb; it.pair = true; it.pc = pc;
+                items.push_back(it);
+                paired[qa] = paired[qb] = 1;
+                q2_launches += pc.passes;
+                q2_max_passes = std::max(q2_max_passes, pc.passes);
+                if (pc.passes > 1) q2_lines = true;
+            }
+        }
+        for (uint64_t q = 0; q < nq; ++q)
+            if (!paired[q]) {
+                WorkItem it;
+                it.qa = it.qb = (uint32_t)q; it.pair = false; it.pc = {0, 0, 0, 0.0};
+                items.push_back(it);
+            }
+    }
+
     SWG_CUDA(ctx, ctx->d_scores.reserve(std::max<uint64_t>(nq * n_pad, 1) * sizeof(int32_t)));
     SWG_CUDA(ctx, ctx->d_profile.reserve((size_t)max_passes * kPassBytes));
     SWG_CUDA(ctx, ctx->d_profile32.reserve((size_t)max_passes * kPassBytes));
     SWG_CUDA(ctx, ctx->d_boundary.reserve(2 * warps * (size_t)(ctx->maxcols + kBoundarySlack) * sizeof(uint2)));
     SWG_CUDA(ctx, ctx->d_counters.reserve(std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t)));
     SWG_CUDA(ctx, ctx->d_resc_list.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
+    const uint64_t dummy_lines = warps * 4 * (uint64_t)(kQ2MinSegCols + kQ2LineSlack);     // one per thread group (G >= 8)
+    if (q2_launches) {
+        SWG_CUDA(ctx, ctx->d_profile_q2.reserve((size_t)q2_max_passes * kQ2ProfileBytes));
+        SWG_CUDA(ctx, ctx->d_resc_list2.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
+        SWG_CUDA(ctx, ctx->d_q2_counters.reserve((size_t)q2_launches * sizeof(uint32_t)));
+        if (q2_lines) SWG_CUDA(ctx, ctx->d_lines.reserve((ctx->line_units + dummy_lines) * sizeof(uint2)));
+    }
     const TopkPlan tp = topk_plan(n_pad, top, nq);
     SWG_CUDA(ctx, ctx->d_topk_scratch.reserve(tp.scratch_keys * sizeof(uint64_t)));
     SWG_CUDA(ctx, ctx->d_top_out.reserve(std::max<uint64_t>(nq * top, 1) * sizeof(uint64_t)));
 
     SWG_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t), ctx->stream));
+    if (q2_launches) SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_q2_counters.p, 0, (size_t)q2_launches * sizeof(uint32_t), ctx->stream));
 
     WfParams p;
     memset(&p, 0, sizeof(p));
@@ -651,14 +790,78 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     p.gap_open_extend = ctx->open_gap + ctx->extend_gap;
     p.gap_extend = ctx->extend_gap;
 
-    while (ctx->q_events.size() < nq + 1) {
+    while (ctx->item_events.size() < items.size() + 1) {
         cudaEvent_t ev;
         SWG_CUDA(ctx, cudaEventCreate(&ev));
-        ctx->q_events.push_back(ev);
+        ctx->item_events.push_back(ev);
     }
-    SWG_CUDA(ctx, cudaEventRecord(ctx->q_events[0], ctx->stream));
+    SWG_CUDA(ctx, cudaEventRecord(ctx->item_events[0], ctx->stream));
     uint64_t padded = 0;
-    for (uint64_t q = 0; q < nq && ctx->ntiles; ++q) {
+    uint32_t q2_next_counter = 0;
+
+    // 32-bit recomputation (K2) of the sequences query q left in `list`
+    auto recompute32 = [&](uint64_t q, uint32_t *list, bool build) -> cudaError_t {
+        const Config wide_cfg = wide_cfgs[q];
+        uint32_t *cnt = ctx->d_counters.as<uint32_t>() + q * 4;
+        cudaError_t e = cudaSuccess;
+        if (build) {
+            e = launch_build_profile(ctx->d_queries.as<int8_t>() + ctx->q_off[q], ctx->q_len[q], ctx->d_submat.as<int8_t>(),
+                                     wide_cfg.G, wide_cfg.K, wide_cfg.passes, ctx->d_profile32.as<uint8_t>(), ctx->stream);
+            ctx->stats.launches += 1;
+        }
+        if (e != cudaSuccess) return e;
+        WfParams r = p;
+        r.scores = ctx->d_scores.as<int32_t>() + q * n_pad;
+        r.profile = ctx->d_profile32.as<uint8_t>();
+        r.passes = wide_cfg.passes;
+        r.tile_first = 0;
+        r.tile_count = ctx->ntiles;
+        r.task_counter = cnt + 2;
+        r.resc_count = cnt + 3;
+        r.resc_list = list;
+        ctx->stats.launches += 1;
+        return launch_wavefront(true, wide_cfg, grid, ctx->stream, r);
+    };
+
+    for (size_t ii = 0; ii < items.size() && ctx->ntiles; ++ii) {
+        const WorkItem &it = items[ii];
+        if (it.pair) {
+            // ---- two queries per register: one launch per pass over the whole shard ----
+            const uint32_t qa = it.qa, qb = it.qb;
+            const PairConfig &pc = it.pc;
+            cudaError_t e = launch_build_profile_q2(ctx->d_queries.as<int8_t>() + ctx->q_off[qa], ctx->q_len[qa],
+                                                    ctx->d_queries.as<int8_t>() + ctx->q_off[qb], ctx->q_len[qb],
+                                                    ctx->d_submat.as<int8_t>(), pc.G, pc.K, pc.passes,
+                                                    ctx->d_profile_q2.as<uint8_t>(), ctx->stream);
+            ctx->stats.launches += 1;
+            WfParams pq = p;
+            pq.scores = ctx->d_scores.as<int32_t>() + (uint64_t)qa * n_pad;
+            pq.scores2 = ctx->d_scores.as<int32_t>() + (uint64_t)qb * n_pad;
+            pq.resc_count = ctx->d_counters.as<uint32_t>() + (uint64_t)qa * 4 + 3;
+            pq.resc_count2 = ctx->d_counters.as<uint32_t>() + (uint64_t)qb * 4 + 3;
+            pq.resc_list = ctx->d_resc_list.as<uint32_t>();
+            pq.resc_list2 = ctx->d_resc_list2.as<uint32_t>();
+            pq.boundary = ctx->d_lines.as<uint2>();
+            pq.line_off = ctx->d_line_off.as<uint64_t>();
+            pq.line_dummy = ctx->line_units;
+            pq.tile_first = 0;
+            pq.tile_count = ctx->ntiles;
+            pq.passes = 1;
+            for (uint32_t pass = 0; pass < pc.passes && e == cudaSuccess; ++pass) {
+                pq.profile = ctx->d_profile_q2.as<uint8_t>() + (size_t)pass * kQ2ProfileBytes;
+                pq.task_counter = ctx->d_q2_counters.as<uint32_t>() + q2_next_counter++;
+                e = launch_q2(pc, pass > 0, pass + 1 < pc.passes, grid, ctx->stream, pq);
+                ctx->stats.launches += 1;
+            }
+            if (e == cudaSuccess) e = recompute32(qa, ctx->d_resc_list.as<uint32_t>(), true);
+            if (e == cudaSuccess) e = recompute32(qb, ctx->d_resc_list2.as<uint32_t>(), true);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "query-pair kernel launch");
+            SWG_CUDA(ctx, cudaEventRecord(ctx->item_events[ii + 1], ctx->stream));
+            ctx->stats.cells += (uint64_t)(ctx->q_len[qa] + ctx->q_len[qb]) * ctx->local_residues;
+            padded += 2ull * pc.passes * pc.G * pc.K * (uint64_t)((ctx->avg_cols + pc.G - 1) * ctx->ntiles) * kTileSeqs;
+            continue;
+        }
+        const uint64_t q = it.qa;
         const uint32_t m = ctx->q_len[q];
         const Config main_cfg = main_cfgs[q];
         const Config wide_cfg = wide_cfgs[q];
@@ -732,17 +935,9 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             ctx->stats.launches += 1;
         }
         if (e == cudaSuccess && forked) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
-        if (e == cudaSuccess) {
-            p.profile = ctx->d_profile32.as<uint8_t>();
-            p.passes = wide_cfg.passes;
-            p.tile_first = 0;
-            p.tile_count = ctx->ntiles;
-            p.task_counter = cnt + 2;
-            e = launch_wavefront(true, wide_cfg, grid, ctx->stream, p);
-            ctx->stats.launches += 1;
-        }
+        if (e == cudaSuccess) e = recompute32(q, ctx->d_resc_list.as<uint32_t>(), false);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "search kernel launch");
-        SWG_CUDA(ctx, cudaEventRecord(ctx->q_events[q + 1], ctx->stream));
+        SWG_CUDA(ctx, cudaEventRecord(ctx->item_events[ii + 1], ctx->stream));
         ctx->stats.cells += (uint64_t)m * ctx->local_residues;
         padded += (uint64_t)main_cfg.passes * main_cfg.G * main_cfg.K *
                   (uint64_t)((ctx->avg_cols + main_cfg.G - 1) * main_tiles) * kTileSeqs;
@@ -775,10 +970,17 @@ int swg_gpu_sync(swg_ctx *ctx)
         ctx->stats.search_seconds = ms_search * 1e-3;
         ctx->stats.topr_seconds = (ms_all - ms_search) * 1e-3;
         ctx->q_seconds.assign(ctx->q_count, 0.0);
-        for (uint64_t q = 0; q < ctx->q_count && ctx->ntiles; ++q) {
+        for (size_t ii = 0; ii < ctx->items.size() && ctx->ntiles; ++ii) {
             float ms = 0.f;
-            SWG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->q_events[q], ctx->q_events[q + 1]));
-            ctx->q_seconds[q] = ms * 1e-3;
+            SWG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->item_events[ii], ctx->item_events[ii + 1]));
+            const WorkItem &it = ctx->items[ii];
+            if (!it.pair) ctx->q_seconds[it.qa] = ms * 1e-3;
+            else {
+                // a pair's time is split in proportion to the cells of its two queries
+                const double la = ctx->q_len[it.qa], lb = ctx->q_len[it.qb], sum = std::max(la + lb, 1.0);
+                ctx->q_seconds[it.qa] = ms * 1e-3 * la / sum;
+                ctx->q_seconds[it.qb] = ms * 1e-3 * lb / sum;
+            }
         }
     }
     return SWG_OK;

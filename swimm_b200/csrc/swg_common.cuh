@@ -44,6 +44,13 @@ constexpr int kTripCols = 4;                 // database columns per trip of the
 constexpr int kBoundarySlack = 64;           // scratch-line columns beyond the longest tile (short segments are padded)
 constexpr int kOverflow16 = 32000;           // a 16-bit lane whose best reaches this is redone in 32 bits
 
+// ---- query-pair kernel (wavefront_q2.cuh): 32-bit profile entries, per-sequence pass lines ----------
+constexpr int kQ2LetterStride = 4096;                       // 1024 rows x 4 bytes
+constexpr int kQ2ProfileBytes = kLetters * kQ2LetterStride; // one pass: 100 KB
+constexpr int kQ2MinSegCols = 48;                           // every segment is padded to at least this many columns (G = 32)
+constexpr int kQ2LineSlack = 8;                             // columns a line extends past its segment (prefetch overrun)
+constexpr uint32_t kQ2MarkSegment = 1u;                     // bit 0 of a column word: first column of a sequence
+
 struct WfParams {
     const uint4 *db;              // tiled database, 16-byte units
     const uint64_t *tile_off;     // [ntiles + 1] in 16-byte units
@@ -62,6 +69,12 @@ struct WfParams {
     uint32_t *resc_list;          // local sequence ids to redo in 32 bits
     int gap_open_extend;          // go + ge
     int gap_extend;               // ge
+    // query-pair kernel (wavefront_q2.cuh) only: the second query's outputs and the per-sequence pass lines
+    int32_t *scores2;             // [ntiles * 16] local scores of the query in the high halves
+    uint32_t *resc_count2;
+    uint32_t *resc_list2;
+    const uint64_t *line_off;     // [ntiles] first line of a tile inside `boundary` (uint2 units); 16 lines per tile
+    uint64_t line_dummy;          // offset of the per-group dummy lines inside `boundary`
 };
 
 __device__ __forceinline__ uint64_t global_seq_index(const WfParams &p, uint32_t local_seq)

@@ -288,8 +288,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
                     const uint32_t pkn = prmt(word, first ? (tag | first_marks) : tag, (j & 1) ? selB : selA);
                     const uint2 hf = ring[j];         // (H, F) entering column c0 + j - 1, processed in this step
                     // the column processed in step j of the next trip (the line has slack past the segment's end:
-                    // entries read there are never used); pass 0 keeps the zeros the ring was initialised with
+                    // entries read there are never used).  In pass 0 nothing is carried in: the slot is cleared during
+                    // the head trips (slot 0 held the previous segment's last column, used once in step 0) and stays zero
                     if (MP && pass > 0) ring[j] = __ldcg(bnd + c0 + j + (NC - 1));
+                    else if (MP && decltype(head_tag)::value) ring[j] = make_uint2(0u, 0u);
                     column(head_tag, pkn, hf, sc + j);
                 }
                 w = nw;

@@ -96,6 +96,31 @@ def test_forced_shapes_vs_oracle(gpu, oracle, G, K):
     assert np.array_equal(got, want), np.argwhere(got != want)[:8]
 
 
+@pytest.mark.parametrize("blocks", [1, 2])
+@pytest.mark.parametrize("qlens,force", [([144, 375, 1000], (0, 0)), ([1500, 2005, 2600], (0, 0)), ([700, 1300], (32, 20)),
+                                         ([9000], (0, 0))])
+def test_many_tasks_per_warp(gpu, oracle, blocks, qlens, force):
+    """Regression: with one or two CTAs every warp runs dozens of tasks back to back, so whatever one task leaves
+    behind (scratch-line columns, the prefetch ring, the carried last column, the running best) meets the next
+    one.  Single-pass, multi-pass and global-profile shapes.  (A ring slot that kept the previous task's last column
+    through pass 0 of the next task once slipped through the few-tasks-per-warp cases.)"""
+    qc, ql, qo, dc, dl, do = _random_case(900 + len(qlens) + blocks, 1200, qlens, mu=4.2, sigma=0.9, hi=1200, plant=0.2)
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    gpu.load_db(dl, dc)
+    gpu.set_option("grid_blocks", blocks)
+    gpu.set_option("query_pairing", 0)
+    gpu.set_option("force_group", force[0])
+    gpu.set_option("force_rows", force[1])
+    try:
+        got, _ = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 0, want_scores=True)
+    finally:
+        gpu.set_option("grid_blocks", 0)
+        gpu.set_option("query_pairing", 1)
+        gpu.set_option("force_group", 0)
+        gpu.set_option("force_rows", 0)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:8]
+
+
 def test_matrix_and_penalty_sweep(gpu, oracle):
     qc, ql, qo, dc, dl, do = _random_case(31, 400, [30, 90, 150, 222])
     gpu.load_db(dl, dc)
