@@ -38,36 +38,36 @@ cudaError_t launch_build_profile(const int8_t *d_query, uint32_t m, const int8_t
     return cudaGetLastError();
 }
 
-// Query-pair profile (wavefront_q2.cuh): one 32-bit entry per (row, letter) holding the scores of BOTH queries,
-//   profile2[pass][letter][ (x/4)*(G*16) + t*16 + (x%4)*4 ] = { s16 S[qB[row]][letter], s16 S[qA[row]][letter] }
-// with row = pass*G*K + t*K + x; rows beyond a query's end score 0 (they can never raise its best).
+// Query-pair profile (wavefront_q2.cuh), one pass: a 32-bit entry per (row, letter) holding the scores of BOTH queries,
+//   profile2[letter][ (x/4)*(G*16) + t*16 + (x%4)*4 ] = { s16 S[qB[row]][letter], s16 S[qA[row]][letter] }
+// with row = row0 + t*K + x; rows beyond a query's end score 0 (they can never raise its best).  The passes of a
+// pair may use different K (the last one is usually shorter), hence one call per pass.
 __global__ void build_profile_q2_kernel(const int8_t *__restrict__ qa, uint32_t ma, const int8_t *__restrict__ qb,
-                                        uint32_t mb, const int8_t *__restrict__ submat, int G, int K, uint32_t passes,
+                                        uint32_t mb, const int8_t *__restrict__ submat, int G, int K, uint32_t row0,
                                         uint32_t *__restrict__ profile)
 {
-    const uint32_t rows_per_pass = (uint32_t)(G * K);
-    const uint32_t total = passes * kLetters * rows_per_pass;
+    const uint32_t rows = (uint32_t)(G * K);
+    const uint32_t total = kLetters * rows;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint32_t rr = i % rows_per_pass;
-        const uint32_t letter = (i / rows_per_pass) % kLetters;
-        const uint32_t pass = i / (rows_per_pass * kLetters);
-        const uint32_t row = pass * rows_per_pass + rr;
+        const uint32_t rr = i % rows;
+        const uint32_t letter = i / rows;
+        const uint32_t row = row0 + rr;
         const uint32_t t = rr / K, x = rr % K;
         int va = 0, vb = 0;
         if (row < ma) va = submat[min((uint32_t)(uint8_t)qa[row], 23u) * 32 + letter];
         if (row < mb) vb = submat[min((uint32_t)(uint8_t)qb[row], 23u) * 32 + letter];
-        profile[((size_t)pass * kQ2ProfileBytes + letter * kQ2LetterStride + (x >> 2) * (G * 16) + t * 16 + (x & 3) * 4) / 4] =
+        profile[(letter * kQ2LetterStride + (x >> 2) * (G * 16) + t * 16 + (x & 3) * 4) / 4] =
             ((uint32_t)va & 0xffffu) | ((uint32_t)vb << 16);
     }
 }
 
 cudaError_t launch_build_profile_q2(const int8_t *d_qa, uint32_t ma, const int8_t *d_qb, uint32_t mb, const int8_t *d_submat,
-                                    int G, int K, uint32_t passes, uint8_t *d_profile, cudaStream_t stream)
+                                    int G, int K, uint32_t row0, uint8_t *d_profile, cudaStream_t stream)
 {
-    const uint32_t total = passes * kLetters * (uint32_t)(G * K);
+    const uint32_t total = kLetters * (uint32_t)(G * K);
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads);
-    build_profile_q2_kernel<<<blocks, threads, 0, stream>>>(d_qa, ma, d_qb, mb, d_submat, G, K, passes,
+    build_profile_q2_kernel<<<blocks, threads, 0, stream>>>(d_qa, ma, d_qb, mb, d_submat, G, K, row0,
                                                             reinterpret_cast<uint32_t *>(d_profile));
     return cudaGetLastError();
 }

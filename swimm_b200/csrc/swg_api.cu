@@ -33,9 +33,11 @@ struct Config {          // how one query is mapped onto thread groups
 };
 
 struct PairConfig {      // how a query pair is mapped onto the query-pair kernel (wavefront_q2.cuh)
-    int G, K;
-    uint32_t passes;
-    double cost;         // estimated run time per database residue (arbitrary units shared with the single-query planner)
+    int G;
+    std::vector<int> K;  // rows per thread of every pass (one launch per pass; a single-pass pair has one entry)
+    double cost;         // estimated run time per database residue (units shared with the single-query planner)
+    uint32_t passes() const { return (uint32_t)K.size(); }
+    uint32_t rows() const { uint32_t r = 0; for (int k : K) r += (uint32_t)(G * k); return r; }
 };
 
 struct WorkItem {        // one entry of a batch's schedule: a single query, or a pair searched by the query-pair kernel
@@ -205,41 +207,70 @@ Config choose_config(uint32_t m, double avg_cols, long force_group, long force_r
     return best;
 }
 
-// Shape of the query-pair kernel for a pair whose longer query has m rows: G in {8, 16, 32}, K in {8, 12, ..., 32},
-// passes = ceil(m / (G*K)); minimises passes * rows / rate like choose_config.
-double q2_rate(int G, int K, uint32_t passes)
+// Shape of the query-pair kernel for a pair whose longer query has m rows.  K is even, 8..32.  One pass when
+// G*K >= m for some G in {8, 16, 32}; otherwise several passes of 32-thread groups, each pass with its own K: the
+// cheapest multiset of pass heights that covers m rows (unbounded knapsack over the measured rates), so that the
+// rows a pair computes exceed its length by less than 64.
+double q2_rate(int G, int K, bool multi)
 {
-    const float *tab = passes > 1 ? kRateQ2Multi_G32 : G == 8 ? kRateQ2_G8 : G == 16 ? kRateQ2_G16 : kRateQ2_G32;
-    return tab[K / 4];
+    const float *tab = multi ? kRateQ2Multi_G32 : G == 8 ? kRateQ2_G8 : G == 16 ? kRateQ2_G16 : kRateQ2_G32;
+    return tab[K / 2];
 }
 
 PairConfig choose_pair_config(uint32_t m, long force_group, long force_rows)
 {
-    PairConfig best = {32, 32, (m + 1023) / 1024, 1e300};
     if (m == 0) m = 1;
+    PairConfig best;
+    best.G = 32;
+    best.cost = 1e300;
     for (int G = 8; G <= 32; G *= 2) {
         if (force_group && G != force_group) continue;
-        for (int K = 8; K <= kMaxRowsPerThread; K += 4) {
+        for (int K = 8; K <= kMaxRowsPerThread; K += 2) {
             if (force_rows && K != force_rows) continue;
-            const uint32_t rows = (uint32_t)(G * K);
-            const uint32_t passes = (m + rows - 1) / rows;
-            if (passes > 1 && G != 32 && !force_group) continue;      // fewer, longer passes: less line traffic
-            // the rate tables count the cells of BOTH queries: cost per database residue = rows * passes / (rate / 2)
-            const double c = 2.0 * passes * rows / q2_rate(G, K, passes);
-            if (c < best.cost) best = {G, K, passes, c};
+            if ((uint32_t)(G * K) < m) continue;
+            // the rate tables count the cells of BOTH queries: cost per database residue = rows / (rate / 2)
+            const double c = 2.0 * G * K / q2_rate(G, K, false);
+            if (c < best.cost) { best.G = G; best.K.assign(1, K); best.cost = c; }
         }
     }
+    if (best.cost < 1e300) return best;
+    // several passes, 32 threads per sequence: min-cost cover of ceil(m / 64) units with passes of K/2 units each
+    const uint32_t units = (m + 63) / 64;
+    std::vector<double> cost(units + 1, 1e300);
+    std::vector<int> pick(units + 1, 0);
+    cost[0] = 0.0;
+    for (uint32_t u = 1; u <= units; ++u)
+        for (int K = 8; K <= kMaxRowsPerThread; K += 2) {
+            if (force_rows && K != force_rows) continue;
+            const uint32_t prev = u > (uint32_t)(K / 2) ? u - K / 2 : 0;
+            const double c = cost[prev] + 2.0 * 32 * K / q2_rate(32, K, true);
+            if (c < cost[u]) { cost[u] = c; pick[u] = K; }
+        }
+    best.G = 32;
+    best.K.clear();
+    for (uint32_t u = units; u > 0;) {
+        const int K = pick[u];
+        best.K.push_back(K);
+        u = u > (uint32_t)(K / 2) ? u - K / 2 : 0;
+    }
+    std::sort(best.K.begin(), best.K.end(), [](int a, int b) { return a > b; });     // tallest passes first
+    best.cost = cost[units];
     return best;
 }
 
-cudaError_t launch_q2(const PairConfig &pc, bool cin, bool cout, int grid, cudaStream_t stream, const WfParams &p)
+cudaError_t launch_q2(int G, int K, bool cin, bool cout, int grid, cudaStream_t stream, const WfParams &p)
 {
-    switch (pc.G) {
-        case 8: return launch_q2_g8(pc.K, cin, cout, grid, stream, p);
-        case 16: return launch_q2_g16(pc.K, cin, cout, grid, stream, p);
-        case 32: return launch_q2_g32(pc.K, cin, cout, grid, stream, p);
-        default: return cudaErrorInvalidValue;
+    if (!cin && !cout) {
+        switch (G) {
+            case 8: return launch_q2_g8(K, grid, stream, p);
+            case 16: return launch_q2_g16(K, grid, stream, p);
+            case 32: return launch_q2_g32(K, grid, stream, p);
+            default: return cudaErrorInvalidValue;
+        }
     }
+    if (G != 32) return cudaErrorInvalidValue;
+    if (!cin) return launch_q2_g32_first(K, grid, stream, p);
+    return cout ? launch_q2_g32_middle(K, grid, stream, p) : launch_q2_g32_last(K, grid, stream, p);
 }
 
 // the 32-thread shape used for long tiles and for the 32-bit re-computation
@@ -460,8 +491,8 @@ int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value)
         if (value != 0 && value != 8 && value != 16 && value != 32) return fail(ctx, SWG_ERR_ARG, "q2_group must be 0, 8, 16 or 32");
         ctx->q2_group = value;
     } else if (!strcmp(name, "q2_rows")) {
-        if (value < 0 || value > kMaxRowsPerThread || value % 4 || value == 4)
-            return fail(ctx, SWG_ERR_ARG, "q2_rows must be 0 or a multiple of 4 in 8..32");
+        if (value < 0 || value > kMaxRowsPerThread || value % 2 || (value > 0 && value < 8))
+            return fail(ctx, SWG_ERR_ARG, "q2_rows must be 0 or an even number in 8..32");
         ctx->q2_rows = value;
     } else if (!strcmp(name, "grid_blocks")) {
         if (value < 0) return fail(ctx, SWG_ERR_ARG, "grid_blocks must be >= 0");
@@ -731,25 +762,29 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                         single += (double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes);
                     }
                     // a sequence is a serial chain of columns: the longest one must not outlast the rest of a launch
-                    const double launch_cycles = (double)pc.G * pc.K * (double)ctx->local_residues /
-                                                 (q2_rate(pc.G, pc.K, pc.passes) * 0.5e9) * kSmHz;
-                    const double step = 4.0 * (12.0 * pc.K + 60.0);
-                    use = pc.cost < single && (double)ctx->maxcols * step < 0.5 * launch_cycles;
+                    bool chain_ok = true;
+                    for (int K : pc.K) {
+                        const double launch_cycles = (double)pc.G * K * (double)ctx->local_residues /
+                                                     (q2_rate(pc.G, K, pc.passes() > 1) * 0.5e9) * kSmHz;
+                        const double step = 4.0 * (12.0 * K + 60.0);
+                        if ((double)ctx->maxcols * step > 0.5 * launch_cycles) chain_ok = false;
+                    }
+                    use = pc.cost < single && chain_ok;
                 }
                 if (!use) continue;
                 WorkItem it;
                 it.qa = qa; it.qb = qb; it.pair = true; it.pc = pc;
                 items.push_back(it);
                 paired[qa] = paired[qb] = 1;
-                q2_launches += pc.passes;
-                q2_max_passes = std::max(q2_max_passes, pc.passes);
-                if (pc.passes > 1) q2_lines = true;
+                q2_launches += pc.passes();
+                q2_max_passes = std::max(q2_max_passes, pc.passes());
+                if (pc.passes() > 1) q2_lines = true;
             }
         }
         for (uint64_t q = 0; q < nq; ++q)
             if (!paired[q]) {
                 WorkItem it;
-                it.qa = it.qb = (uint32_t)q; it.pair = false; it.pc = {0, 0, 0, 0.0};
+                it.qa = it.qb = (uint32_t)q; it.pair = false; it.pc.G = 0; it.pc.cost = 0.0;
                 items.push_back(it);
             }
     }
@@ -829,11 +864,16 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             // ---- two queries per register: one launch per pass over the whole shard ----
             const uint32_t qa = it.qa, qb = it.qb;
             const PairConfig &pc = it.pc;
-            cudaError_t e = launch_build_profile_q2(ctx->d_queries.as<int8_t>() + ctx->q_off[qa], ctx->q_len[qa],
-                                                    ctx->d_queries.as<int8_t>() + ctx->q_off[qb], ctx->q_len[qb],
-                                                    ctx->d_submat.as<int8_t>(), pc.G, pc.K, pc.passes,
-                                                    ctx->d_profile_q2.as<uint8_t>(), ctx->stream);
-            ctx->stats.launches += 1;
+            cudaError_t e = cudaSuccess;
+            uint32_t row0 = 0;
+            for (uint32_t pass = 0; pass < pc.passes() && e == cudaSuccess; ++pass) {
+                e = launch_build_profile_q2(ctx->d_queries.as<int8_t>() + ctx->q_off[qa], ctx->q_len[qa],
+                                            ctx->d_queries.as<int8_t>() + ctx->q_off[qb], ctx->q_len[qb],
+                                            ctx->d_submat.as<int8_t>(), pc.G, pc.K[pass], row0,
+                                            ctx->d_profile_q2.as<uint8_t>() + (size_t)pass * kQ2ProfileBytes, ctx->stream);
+                row0 += (uint32_t)(pc.G * pc.K[pass]);
+                ctx->stats.launches += 1;
+            }
             WfParams pq = p;
             pq.scores = ctx->d_scores.as<int32_t>() + (uint64_t)qa * n_pad;
             pq.scores2 = ctx->d_scores.as<int32_t>() + (uint64_t)qb * n_pad;
@@ -847,10 +887,10 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             pq.tile_first = 0;
             pq.tile_count = ctx->ntiles;
             pq.passes = 1;
-            for (uint32_t pass = 0; pass < pc.passes && e == cudaSuccess; ++pass) {
+            for (uint32_t pass = 0; pass < pc.passes() && e == cudaSuccess; ++pass) {
                 pq.profile = ctx->d_profile_q2.as<uint8_t>() + (size_t)pass * kQ2ProfileBytes;
                 pq.task_counter = ctx->d_q2_counters.as<uint32_t>() + q2_next_counter++;
-                e = launch_q2(pc, pass > 0, pass + 1 < pc.passes, grid, ctx->stream, pq);
+                e = launch_q2(pc.G, pc.K[pass], pass > 0, pass + 1 < pc.passes(), grid, ctx->stream, pq);
                 ctx->stats.launches += 1;
             }
             if (e == cudaSuccess) e = recompute32(qa, ctx->d_resc_list.as<uint32_t>(), true);
@@ -858,7 +898,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             if (e != cudaSuccess) return cuda_fail(ctx, e, "query-pair kernel launch");
             SWG_CUDA(ctx, cudaEventRecord(ctx->item_events[ii + 1], ctx->stream));
             ctx->stats.cells += (uint64_t)(ctx->q_len[qa] + ctx->q_len[qb]) * ctx->local_residues;
-            padded += 2ull * pc.passes * pc.G * pc.K * (uint64_t)((ctx->avg_cols + pc.G - 1) * ctx->ntiles) * kTileSeqs;
+            padded += 2ull * pc.rows() * (uint64_t)((ctx->avg_cols + pc.G - 1) * ctx->ntiles) * kTileSeqs;
             continue;
         }
         const uint64_t q = it.qa;

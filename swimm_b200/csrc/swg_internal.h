@@ -17,9 +17,9 @@ cudaError_t launch_build_tiles(const int8_t *d_residues, const uint64_t *d_seq_o
 cudaError_t launch_build_profile(const int8_t *d_query, uint32_t m, const int8_t *d_submat, int G, int K,
                                  uint32_t passes, uint8_t *d_profile, cudaStream_t stream);
 
-// profile.cu: the query-pair profile, [passes][25][4096] bytes (wavefront_q2.cuh); every entry a shape reads is written
+// profile.cu: one pass of the query-pair profile, [25][4096] bytes (wavefront_q2.cuh), rows row0 .. row0 + G*K - 1
 cudaError_t launch_build_profile_q2(const int8_t *d_qa, uint32_t ma, const int8_t *d_qb, uint32_t mb, const int8_t *d_submat,
-                                    int G, int K, uint32_t passes, uint8_t *d_profile, cudaStream_t stream);
+                                    int G, int K, uint32_t row0, uint8_t *d_profile, cudaStream_t stream);
 
 // topk.cu: top-r selection on 64-bit keys (score << 32 | global index), descending, all queries of a batch
 struct TopkPlan {

@@ -37,10 +37,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
     typedef uint32_t reg;
     typedef Lane16 L;
     static_assert(G == 8 || G == 16 || G == 32, "group size");
-    static_assert(K >= 4 && K <= kMaxRowsPerThread && K % 4 == 0, "rows per thread");
+    static_assert(K >= 2 && K <= kMaxRowsPerThread && K % 2 == 0, "rows per thread");
     constexpr int GPW = 32 / G;                       // groups per warp
     constexpr int TPT = kTileSeqs / GPW;              // warp tasks per tile: every group takes one sequence
-    constexpr int KCH = K / 4;                        // 4-row (16-byte) profile chunks per thread
+    constexpr int KCH = (K + 3) / 4;                  // 4-row (16-byte) profile chunks per thread
     constexpr int NC = kTripCols;
     constexpr uint32_t FI = G / NC;
     constexpr uint32_t kMinTrips = FI + 4;
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.profile);
         uint4 *dst = reinterpret_cast<uint4 *>(prof_smem);
-        // only the G*K*4 bytes of a letter row that this shape reads
-        constexpr int row16 = G * K * 4 / 16;
+        // only the part of a letter row that this shape reads
+        constexpr int row16 = G * KCH;
         for (int i = threadIdx.x; i < kLetters * row16; i += blockDim.x) {
             const int letter = i / row16, o = i % row16;
             dst[letter * (kQ2LetterStride / 16) + o] = src[letter * (kQ2LetterStride / 16) + o];
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int x = 4 * i + k;
+                if (x >= K) continue;                          // K = 4n + 2: the last chunk is half used
                 const uint32_t wx = k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w;
                 const reg ds = DS[x];
                 const reg h = L::max3_relu(ds, E[x], f);       // max(ds, E(i,j), F(i,j), 0)
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
 #pragma unroll
             for (int i = 0; i < KCH; ++i) {
                 const uint4 v = q[i * G];
-                DS[4 * i] = v.x; DS[4 * i + 1] = v.y; DS[4 * i + 2] = v.z; DS[4 * i + 3] = v.w;
+                DS[4 * i] = v.x; DS[4 * i + 1] = v.y;
+                if (4 * i + 2 < K) { DS[4 * i + 2] = v.z; DS[4 * i + 3] = v.w; }
             }
 #pragma unroll
             for (int x = 0; x < K; ++x) E[x] = L::splat(0);
@@ -236,10 +238,14 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
     }
 }
 
-// host-side launchers (wavefront_q2_inst_*.cu); K in {8, 12, ..., 32}
-cudaError_t launch_q2_g8(int K, bool cin, bool cout, int grid, cudaStream_t stream, const WfParams &p);
-cudaError_t launch_q2_g16(int K, bool cin, bool cout, int grid, cudaStream_t stream, const WfParams &p);
-cudaError_t launch_q2_g32(int K, bool cin, bool cout, int grid, cudaStream_t stream, const WfParams &p);
+// host-side launchers (wavefront_q2_inst_*.cu); K even, 8..32.  Groups of 8 and 16 threads are instantiated for
+// single-pass pairs only (a pair that needs several passes always runs 32-thread groups: fewer, longer passes).
+cudaError_t launch_q2_g8(int K, int grid, cudaStream_t stream, const WfParams &p);
+cudaError_t launch_q2_g16(int K, int grid, cudaStream_t stream, const WfParams &p);
+cudaError_t launch_q2_g32(int K, int grid, cudaStream_t stream, const WfParams &p);
+cudaError_t launch_q2_g32_first(int K, int grid, cudaStream_t stream, const WfParams &p);    // pass 0 of several
+cudaError_t launch_q2_g32_middle(int K, int grid, cudaStream_t stream, const WfParams &p);
+cudaError_t launch_q2_g32_last(int K, int grid, cudaStream_t stream, const WfParams &p);
 
 template <int G, int K, bool CIN, bool COUT, int GOE = 0, int GE = 0>
 cudaError_t launch_q2_one(int grid, cudaStream_t stream, const WfParams &p)
@@ -257,34 +263,24 @@ cudaError_t launch_q2_one(int grid, cudaStream_t stream, const WfParams &p)
     return cudaGetLastError();
 }
 
-template <int G, int K>
-cudaError_t launch_q2_shape(bool cin, bool cout, int grid, cudaStream_t stream, const WfParams &p)
+template <int G, bool CIN, bool COUT>
+cudaError_t launch_q2_family(int K, int grid, cudaStream_t stream, const WfParams &p)
 {
-    const bool fast = p.gap_open_extend == kFastGapOpenExtend && p.gap_extend == kFastGapExtend;
     constexpr int FO = kFastGapOpenExtend, FE = kFastGapExtend;
-    if (fast) {
-        if (!cin && !cout) return launch_q2_one<G, K, false, false, FO, FE>(grid, stream, p);
-        if (!cin && cout) return launch_q2_one<G, K, false, true, FO, FE>(grid, stream, p);
-        if (cin && cout) return launch_q2_one<G, K, true, true, FO, FE>(grid, stream, p);
-        return launch_q2_one<G, K, true, false, FO, FE>(grid, stream, p);
+    if (p.gap_open_extend == FO && p.gap_extend == FE) {
+        switch (K) {
+#define SWG_CASE(k) case k: return launch_q2_one<G, k, CIN, COUT, FO, FE>(grid, stream, p);
+            SWG_CASE(8) SWG_CASE(10) SWG_CASE(12) SWG_CASE(14) SWG_CASE(16) SWG_CASE(18) SWG_CASE(20)
+            SWG_CASE(22) SWG_CASE(24) SWG_CASE(26) SWG_CASE(28) SWG_CASE(30) SWG_CASE(32)
+#undef SWG_CASE
+            default: return cudaErrorInvalidValue;
+        }
     }
-    if (!cin && !cout) return launch_q2_one<G, K, false, false>(grid, stream, p);
-    if (!cin && cout) return launch_q2_one<G, K, false, true>(grid, stream, p);
-    if (cin && cout) return launch_q2_one<G, K, true, true>(grid, stream, p);
-    return launch_q2_one<G, K, true, false>(grid, stream, p);
-}
-
-template <int G>
-cudaError_t launch_q2_group(int K, bool cin, bool cout, int grid, cudaStream_t stream, const WfParams &p)
-{
     switch (K) {
-        case 8: return launch_q2_shape<G, 8>(cin, cout, grid, stream, p);
-        case 12: return launch_q2_shape<G, 12>(cin, cout, grid, stream, p);
-        case 16: return launch_q2_shape<G, 16>(cin, cout, grid, stream, p);
-        case 20: return launch_q2_shape<G, 20>(cin, cout, grid, stream, p);
-        case 24: return launch_q2_shape<G, 24>(cin, cout, grid, stream, p);
-        case 28: return launch_q2_shape<G, 28>(cin, cout, grid, stream, p);
-        case 32: return launch_q2_shape<G, 32>(cin, cout, grid, stream, p);
+#define SWG_CASE(k) case k: return launch_q2_one<G, k, CIN, COUT>(grid, stream, p);
+        SWG_CASE(8) SWG_CASE(10) SWG_CASE(12) SWG_CASE(14) SWG_CASE(16) SWG_CASE(18) SWG_CASE(20)
+        SWG_CASE(22) SWG_CASE(24) SWG_CASE(26) SWG_CASE(28) SWG_CASE(30) SWG_CASE(32)
+#undef SWG_CASE
         default: return cudaErrorInvalidValue;
     }
 }

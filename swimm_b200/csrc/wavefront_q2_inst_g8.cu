@@ -1,12 +1,12 @@
-// wavefront_q2_inst_g8.cu -- instantiations of wavefront_q2_kernel<8, K, ...> for K = 8, 12, ..., 32 (one file per
-// group size so that the families compile in parallel).
+// wavefront_q2_inst_g8.cu -- instantiations of wavefront_q2_kernel<8, K, false, false> for K = 8, 10, ..., 32: single-pass pairs, 8-thread groups
+// (one file per family so that the families compile in parallel).
 #include "wavefront_q2.cuh"
 
 namespace swg {
 
-cudaError_t launch_q2_g8(int K, bool cin, bool cout, int grid, cudaStream_t stream, const WfParams &p)
+cudaError_t launch_q2_g8(int K, int grid, cudaStream_t stream, const WfParams &p)
 {
-    return launch_q2_group<8>(K, cin, cout, grid, stream, p);
+    return launch_q2_family<8, false, false>(K, grid, stream, p);
 }
 
 }  // namespace swg
