@@ -303,39 +303,58 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline: the integer/SIMD pipe for this instruction mix, measured live ----
+    # ---- roofline: the integer/SIMD pipe for each kernel's own instruction mix, measured live ----
     roof = None
     if not args.no_pipebench:
         pb = s.pipebench()
-        # default penalties (10/2) run the kernels whose penalties are immediate operands: the matching probe
-        mix = pb["probes"]["mix_v2_immediate_penalties" if (GO + GE, GE) == (12, 2) else "mix_v2_4p5_alu_2_viadd"]
-        # the kernel's own 6.5 integer instructions per 2 cells (one s16x2 lane pair), dependency-free:
-        # peak cells/s = instr/s * 2 / 6.5
-        peak_gcups = mix["ginstr_per_s"] * 2.0 / 6.5
+        fast = (GO + GE, GE) == (12, 2)         # default penalties run the kernels whose penalties are immediates
+        kinds = s.query_kernels()
+        kernels = {}
+        # sequence-pair kernel: 6.5 integer instructions per 2 cells; query-pair kernel: 5.5 (no score-pack PRMT).
+        # peak cells/s = dependency-free issue rate of that mix * 2 / instructions per cell pair
+        for kind, name, probe, ipc2, mix_text in [
+                (0, "wavefront_kernel<Lane16,G,K> (one query x two database sequences per register)",
+                 "mix_v2_immediate_penalties" if fast else "mix_v2_4p5_alu_2_viadd", 6.5,
+                 "6.5 integer instr per 2 cells: 4.5 on the ALU pipe (PRMT, VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + 2 VIADD.16x2"),
+                (1, "wavefront_q2_kernel<G,K> (two queries x one database sequence per register)",
+                 "mix_q2_3p5alu_2viadd_immediate" if fast else "mix_c_hef_best_3p5alu_2viadd", 5.5,
+                 "5.5 integer instr per 2 cells: 3.5 on the ALU pipe (VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + 2 VIADD.16x2")]:
+            sel = kinds == kind
+            secs = float(q_secs[sel].sum())
+            if secs <= 0:
+                continue
+            mix = pb["probes"][probe]
+            cells_k = float(ql[sel].astype(np.int64).sum()) * len(dc) * args.steps
+            peak = mix["ginstr_per_s"] * 2.0 / ipc2
+            kernels[kind] = {"kernel": name, "queries": int(sel.sum()), "share_of_search_time": secs / float(q_secs.sum()),
+                             "achieved": cells_k / secs / 1e9, "peak": peak, "frac": cells_k / secs / 1e9 / peak,
+                             "mix": mix_text + "; measured %.1f thread-instr/clk/SM at %.0f MHz"
+                                    % (mix["thread_instr_per_clk_per_sm"], mix["sm_mhz"])}
+        dom = max(kernels.values(), key=lambda k: k["share_of_search_time"])
+        others = [k for k in kernels.values() if k is not dom]
         per_gpu = cells_local * args.steps / dev_s / 1e9
-        search_gcups = cells_local * args.steps / search_s / 1e9
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] \
             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        db_bytes = st["db_bytes"]
-        algo_gbs = db_bytes * q.n * args.steps / search_s / 1e9     # every query streams the tiled database once
-        # DRAM traffic of one search launch from the committed ncu --set full capture (bytes read + written)
-        traffic = None
+        # algorithmic HBM bytes: the tiled database once per search launch + the pass lines of the query-pair kernel
+        algo_gbs = st["stream_bytes"] * args.steps / search_s / 1e9
+        # DRAM traffic of the dominant kernel's launches from the committed ncu --set full captures (read + written)
+        traffic, traffic_note = None, None
         try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_cfg2_three_kernels.json")))["q144"]
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_cfg2_kernels.json")))
             unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            traffic = sum(float(cap[k].split()[0]) * unit[cap[k].split()[1]]
+            key = "q2_single_pass" if dom is kernels.get(1) else "seqpair_q144"
+            traffic = sum(float(cap[key][k].split()[0]) * unit[cap[key][k].split()[1]]
                           for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            traffic_note = ("ncu dram bytes read+written by one full-size launch (profiles/r01_ncu_full_cfg2_kernels.json, %s); "
+                            "algorithmic bytes of that launch = the tiled database, %d; a middle pass of the query-pair kernel "
+                            "also reads and writes its pass lines, 8 B per database column each way (q2_middle_pass)"
+                            % (key, st["db_bytes"]))
         except Exception:
             pass
-        roof = {"bound": "int_alu", "achieved": search_gcups, "peak": peak_gcups, "unit": "GCUPS",
-                "frac": search_gcups / peak_gcups, "traffic": traffic,
-                "traffic_note": "ncu dram bytes read+written by one full-size search launch (profiles/r01_ncu_full_cfg2_three_"
-                                "kernels.json, q144); algorithmic bytes per launch = the tiled database, %d" % db_bytes,
-                "kernel": "wavefront_kernel<Lane16,G,K> (all 16-bit search launches of a step)",
-                "mix": "6.5 integer instr per 2 cells: 4.5 on the ALU pipe (PRMT, VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + "
-                       "2 VIADD.16x2 (gap penalties as immediates); measured %.1f thread-instr/clk/SM at %.0f MHz"
-                       % (mix["thread_instr_per_clk_per_sm"], mix["sm_mhz"]),
-                "whole_step_gcups_per_gpu": per_gpu,
+        roof = {"bound": "int_alu", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "GCUPS",
+                "frac": dom["frac"], "traffic": traffic, "traffic_note": traffic_note,
+                "kernel": dom["kernel"], "mix": dom["mix"], "share_of_search_time": dom["share_of_search_time"],
+                "other_kernels": others, "whole_step_gcups_per_gpu": per_gpu,
                 "hbm": {"bound": "hbm", "achieved": algo_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": algo_gbs / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json"))
                         else "fallback"},

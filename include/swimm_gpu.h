@@ -55,6 +55,9 @@ typedef struct {
     uint64_t db_bytes;         /* bytes of the resident tiled database on this device */
     uint64_t h2d_bytes;        /* host->device bytes of the last search call */
     uint64_t d2h_bytes;        /* device->host bytes of the last search call */
+    uint64_t pair_launches;    /* launches of the query-pair kernel in the last run (one per pass of a query pair) */
+    uint64_t stream_bytes;     /* algorithmic HBM bytes of the last run's search launches: the tiled database once per
+                                  launch + the pass lines the query-pair kernel parks and re-reads (8 B per column each way) */
 } swg_stats;
 
 /* ---- context ---- */
@@ -104,6 +107,10 @@ int swg_gpu_sync(swg_ctx *ctx);                                   /* wait only *
 int swg_gpu_get_stats(swg_ctx *ctx, swg_stats *out);
 /* device time (CUDA events) of each query's kernels in the last completed run, in the order the queries were given */
 int swg_gpu_get_query_seconds(swg_ctx *ctx, double *seconds, uint64_t max_queries);
+
+/* which kernel searched each query in the last run, in the order the queries were given: 0 = sequence-pair kernel
+ * (one query, two database sequences per register), 1 = query-pair kernel (two queries of a batch per register) */
+int swg_gpu_get_query_kernels(swg_ctx *ctx, int32_t *kind, uint64_t max_queries);
 
 /* Measured issue rates of the search kernel's instruction mix (the integer roofline the search is
  * reported against).  ginstr_per_s[p] = 1e9 thread-instructions per second on the whole GPU for probe p,

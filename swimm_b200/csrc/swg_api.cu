@@ -726,6 +726,8 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     ctx->stats.cells = 0;
     ctx->stats.padded_cells = 0;
     ctx->stats.rescored = 0;
+    ctx->stats.pair_launches = 0;
+    ctx->stats.stream_bytes = 0;
 
     const int grid = ctx->grid_blocks > 0 ? (int)std::min<long>(ctx->grid_blocks, ctx->sm_count) : ctx->sm_count;
     const int warps_per_block = kBlockThreads / 32;
@@ -892,6 +894,9 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 pq.task_counter = ctx->d_q2_counters.as<uint32_t>() + q2_next_counter++;
                 e = launch_q2(pc.G, pc.K[pass], pass > 0, pass + 1 < pc.passes(), grid, ctx->stream, pq);
                 ctx->stats.launches += 1;
+                ctx->stats.pair_launches += 1;
+                ctx->stats.stream_bytes += ctx->db_units * sizeof(uint4) +
+                                           ((pass > 0) + (pass + 1 < pc.passes())) * ctx->line_units * sizeof(uint2);
             }
             if (e == cudaSuccess) e = recompute32(qa, ctx->d_resc_list.as<uint32_t>(), true);
             if (e == cudaSuccess) e = recompute32(qb, ctx->d_resc_list2.as<uint32_t>(), true);
@@ -979,6 +984,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         if (e != cudaSuccess) return cuda_fail(ctx, e, "search kernel launch");
         SWG_CUDA(ctx, cudaEventRecord(ctx->item_events[ii + 1], ctx->stream));
         ctx->stats.cells += (uint64_t)m * ctx->local_residues;
+        ctx->stats.stream_bytes += ctx->db_units * sizeof(uint4);
         padded += (uint64_t)main_cfg.passes * main_cfg.G * main_cfg.K *
                   (uint64_t)((ctx->avg_cols + main_cfg.G - 1) * main_tiles) * kTileSeqs;
     }
@@ -1092,6 +1098,18 @@ int swg_gpu_get_query_seconds(swg_ctx *ctx, double *seconds, uint64_t max_querie
 {
     if (!ctx || !seconds) return fail(ctx, SWG_ERR_ARG, "NULL argument");
     for (uint64_t q = 0; q < max_queries; ++q) seconds[q] = q < ctx->q_seconds.size() ? ctx->q_seconds[q] : 0.0;
+    return SWG_OK;
+}
+
+int swg_gpu_get_query_kernels(swg_ctx *ctx, int32_t *kind, uint64_t max_queries)
+{
+    if (!ctx || !kind) return fail(ctx, SWG_ERR_ARG, "NULL argument");
+    for (uint64_t q = 0; q < max_queries; ++q) kind[q] = 0;
+    for (const WorkItem &it : ctx->items)
+        if (it.pair) {
+            if (it.qa < max_queries) kind[it.qa] = 1;
+            if (it.qb < max_queries) kind[it.qb] = 1;
+        }
     return SWG_OK;
 }
 

@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libswimm_cuda.so")
 ABI_SYMBOLS = [
     "swg_gpu_device_count", "swg_gpu_create", "swg_gpu_destroy", "swg_gpu_last_error", "swg_gpu_load_db",
     "swg_gpu_load_db_shard", "swg_gpu_load_db_interleaved", "swg_gpu_db_local_sequences", "swg_gpu_db_local_residues", "swg_gpu_search",
-    "swg_gpu_set_queries", "swg_gpu_run", "swg_gpu_fetch", "swg_gpu_sync", "swg_gpu_get_stats", "swg_gpu_get_query_seconds", "swg_gpu_pipebench",
+    "swg_gpu_set_queries", "swg_gpu_run", "swg_gpu_fetch", "swg_gpu_sync", "swg_gpu_get_stats", "swg_gpu_get_query_seconds",
+    "swg_gpu_get_query_kernels", "swg_gpu_pipebench",
     "swg_gpu_set_option", "swg_gpu_debug_read", "swimm_gpu_search_avx2_compat",
 ]
 
@@ -30,7 +31,7 @@ class Stats(C.Structure):
     _fields_ = [("device_seconds", C.c_double), ("search_seconds", C.c_double), ("topr_seconds", C.c_double),
                 ("cells", C.c_uint64), ("padded_cells", C.c_uint64), ("launches", C.c_uint64),
                 ("rescored", C.c_uint64), ("db_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64), ("pair_launches", C.c_uint64), ("stream_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -68,6 +69,7 @@ def load_library() -> C.CDLL:
     L.swg_gpu_sync.argtypes = [vp]
     L.swg_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.swg_gpu_get_query_seconds.argtypes = [vp, vp, u64]
+    L.swg_gpu_get_query_kernels.argtypes = [vp, vp, u64]
     L.swg_gpu_pipebench.argtypes = [vp, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.swg_gpu_debug_read.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     L.swg_gpu_set_option.argtypes = [vp, C.c_char_p, C.c_long]
@@ -205,6 +207,12 @@ class GpuSearch:
     def query_seconds(self) -> np.ndarray:
         out = np.zeros(self.q_count, dtype=np.float64)
         self._check(self.L.swg_gpu_get_query_seconds(self.ctx, out.ctypes.data, self.q_count), "get_query_seconds")
+        return out
+
+    def query_kernels(self) -> np.ndarray:
+        """0 = sequence-pair kernel, 1 = query-pair kernel, per query of the last run."""
+        out = np.zeros(self.q_count, dtype=np.int32)
+        self._check(self.L.swg_gpu_get_query_kernels(self.ctx, out.ctypes.data, self.q_count), "get_query_kernels")
         return out
 
     def debug_read(self, name: str, dtype=np.uint8) -> np.ndarray:

@@ -15,9 +15,11 @@ s = gpu.GpuSearch(0)
 s.load_db(dl, dc)
 s.set_option("query_pairing", 2)
 res = {}
-for G in (8, 16, 32):
+Gs = [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 else '8,16,32'.split(','))]
+Ks = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else list(range(8, 33, 2))
+for G in Gs:
     res[G] = {}
-    for K in range(8, 33, 2):
+    for K in Ks:
         out = []
         for passes in ([1, 3] if G == 32 else [1]):
             m = G * K * passes

@@ -15,7 +15,9 @@ for row in csv.DictReader(lines):
     v *= {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}[row["Metric Unit"]]
     k = re.sub(r"\(.*", "", row["Kernel Name"])
     k = re.sub(r"void |swg::|\(anonymous namespace\)::|<unnamed>::", "", k)
+    k = re.sub(r"\((?:int|bool)\)", "", k)
     fam = re.sub(r"wavefront_kernel<(Lane\d+), (\d+), (\d+), (\d), (\d), (\d+), (\d+)>", r"wavefront_kernel<\1,G=\2,K=*,MP=\4,GP=\5,imm=\6/\7>", k)
+    fam = re.sub(r"wavefront_q2_kernel<(\d+), (\d+), (\d), (\d), (\d+), (\d+)>", r"wavefront_q2_kernel<G=\1,K=*,CIN=\3,COUT=\4,imm=\5/\6>", fam)
     tot[fam] += v; cnt[fam] += 1
 T = sum(tot.values())
 with open(os.path.join(P, tag + "_launch_list_summary.txt"), "w") as f:
@@ -36,8 +38,9 @@ keys = ["gpu__time_duration.sum", "sm__inst_executed_pipe_alu.avg.pct_of_peak_su
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
 res = {}
-for i, name in [(1, "q144"), (2, "q1000"), (3, "q_multi_pass")]:
-    rep = os.path.join(G, "prof2_%d.ncu-rep" % i)
+keys += ["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
+for i, name in [(1, "q2_single_pass"), (2, "q2_middle_pass"), (3, "q2_last_pass"), (4, "seqpair_q144")]:
+    rep = os.path.join(G, "prof3_%d.ncu-rep" % i)
     if not os.path.exists(rep):
         continue
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -45,7 +48,7 @@ for i, name in [(1, "q144"), (2, "q1000"), (3, "q_multi_pass")]:
     hdr, units, d = rows[0], rows[1], rows[2]
     idx = {h: j for j, h in enumerate(hdr)}
     res[name] = {"kernel": d[idx["Kernel Name"]], **{k: (d[idx[k]] + " " + units[idx[k]]).strip() for k in keys if k in idx}}
-json.dump(res, open(os.path.join(P, tag + "_ncu_full_cfg2_three_kernels.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(P, tag + "_ncu_full_cfg2_kernels.json"), "w"), indent=1)
 for k, v in res.items():
     print(k, v["kernel"], v["gpu__time_duration.sum"], "ALU", v["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"],
           "issue", v["smsp__issue_active.avg.pct_of_peak_sustained_active"], "dram rd", v["dram__bytes_read.sum"], "wr", v["dram__bytes_write.sum"])
