@@ -40,10 +40,23 @@ struct PairConfig {      // how a query pair is mapped onto the query-pair kerne
     uint32_t rows() const { uint32_t r = 0; for (int k : K) r += (uint32_t)(G * k); return r; }
 };
 
-struct WorkItem {        // one entry of a batch's schedule: a single query, or a pair searched by the query-pair kernel
-    uint32_t qa, qb;     // query indices (qb unused for a single query)
-    bool pair;
-    PairConfig pc;
+struct LaneSlice {       // what one 16-bit lane does in one launch of the query-pair kernel
+    int32_t q;           // query index, -1: the lane is idle
+    uint32_t row0;       // first row of the query this launch computes
+    bool first, last;    // the query's first / last launch
+};
+
+struct Q2Launch {
+    int G, K;
+    LaneSlice lane[2];
+};
+
+struct WorkItem {        // one entry of a batch's schedule
+    bool pair;           // false: query qa on the sequence-pair kernel; true: a group of queries on the query-pair kernel
+    uint32_t qa;
+    std::vector<uint32_t> members;      // the group's queries
+    std::vector<Q2Launch> launches;     // the group's launches, in stream order
+    uint64_t member_rows = 0;
 };
 
 struct DeviceBuf {
@@ -116,6 +129,7 @@ struct swg_ctx {
     long force_group = 0, force_rows = 0;
     long query_pairing = 1;                 // 0: never pair queries, 1: pair when the planner expects a gain, 2: always
     long q2_group = 0, q2_rows = 0;         // forced shape of the query-pair kernel (0: planner)
+    long verbose = 0;                       // 1: print the schedule of every run to stderr
     long grid_blocks = 0;                   // CTAs per search launch (0: one per SM); small values make every warp run many tasks
 
     swg_stats stats;
@@ -256,6 +270,53 @@ PairConfig choose_pair_config(uint32_t m, long force_group, long force_rows)
     std::sort(best.K.begin(), best.K.end(), [](int a, int b) { return a > b; });     // tallest passes first
     best.cost = cost[units];
     return best;
+}
+
+// The two lanes as independent streams of queries.  `lanes[l]` lists lane l's queries in order; every launch computes
+// 32*K rows of both lanes' current queries.  Launch boundaries are put where a query ends (the other lane simply
+// continues), so the rows a lane computes exceed its queries' lengths by < 64 per query plus the idle tail of the
+// shorter lane.  Returns the launches and their estimated cost (same units as PairConfig::cost).
+double plan_stream(const std::vector<uint32_t> lanes[2], const std::vector<uint16_t> &q_len, long force_rows,
+                   std::vector<Q2Launch> &out)
+{
+    size_t pos[2] = {0, 0};
+    uint32_t done[2] = {0, 0};
+    double cost = 0.0;
+    for (;;) {
+        int32_t q[2];
+        uint32_t rem[2];
+        for (int l = 0; l < 2; ++l) {
+            q[l] = pos[l] < lanes[l].size() ? (int32_t)lanes[l][pos[l]] : -1;
+            rem[l] = q[l] >= 0 ? std::max<uint32_t>(q_len[q[l]], 1u) - done[l] : 0xffffffffu;
+        }
+        if (q[0] < 0 && q[1] < 0) break;
+        uint32_t seg = std::min(rem[0], rem[1]);
+        const uint32_t far = std::max(rem[0], rem[1]);
+        if (far != 0xffffffffu && far - seg <= 192) seg = far;       // ends this close finish in the same launches
+        const PairConfig pc = choose_pair_config(seg, 32, force_rows);
+        bool fin[2] = {false, false};
+        for (int K : pc.K) {
+            Q2Launch L;
+            L.G = pc.G;
+            L.K = K;
+            const uint32_t rows = (uint32_t)(pc.G * K);
+            for (int l = 0; l < 2; ++l) {
+                if (q[l] >= 0 && !fin[l]) {
+                    const uint32_t len = std::max<uint32_t>(q_len[q[l]], 1u);
+                    L.lane[l] = {q[l], done[l], done[l] == 0, done[l] + rows >= len};
+                    done[l] += rows;
+                    fin[l] = L.lane[l].last;
+                } else {
+                    L.lane[l] = {-1, 0, false, false};
+                }
+            }
+            out.push_back(L);
+            cost += 2.0 * rows / q2_rate(pc.G, K, true);
+        }
+        for (int l = 0; l < 2; ++l)
+            if (fin[l]) { ++pos[l]; done[l] = 0; }
+    }
+    return cost;
 }
 
 cudaError_t launch_q2(int G, int K, bool cin, bool cout, int grid, cudaStream_t stream, const WfParams &p)
@@ -494,6 +555,8 @@ int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value)
         if (value < 0 || value > kMaxRowsPerThread || value % 2 || (value > 0 && value < 8))
             return fail(ctx, SWG_ERR_ARG, "q2_rows must be 0 or an even number in 8..32");
         ctx->q2_rows = value;
+    } else if (!strcmp(name, "verbose")) {
+        ctx->verbose = value;
     } else if (!strcmp(name, "grid_blocks")) {
         if (value < 0) return fail(ctx, SWG_ERR_ARG, "grid_blocks must be >= 0");
         ctx->grid_blocks = value;
@@ -740,57 +803,127 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         max_passes = std::max(max_passes, std::max(main_cfgs[q].passes, wide_cfgs[q].passes));
     }
 
-    // ---- schedule: queries of similar length are paired and searched by the query-pair kernel when the planner
-    // expects that to be faster than two runs of the sequence-pair kernel; the others run one by one ----
+    // ---- schedule ----
+    // Batches of at least two queries use the query-pair kernel where the planner expects it to beat the
+    // sequence-pair kernel: (1) the queries longer than one pass (1024 rows) are dealt to the two 16-bit lanes
+    // (longest first, to the lane with fewer rows) and run as two streams, pass by pass; (2) the shorter ones are
+    // paired with their neighbour in length for one single-pass launch.  Everything else runs one query at a time.
     std::vector<WorkItem> &items = ctx->items;
     items.clear();
-    uint32_t q2_launches = 0, q2_max_passes = 0;
+    uint32_t q2_launches = 0;
     bool q2_lines = false;
     {
         std::vector<uint32_t> order(nq);
         for (uint64_t q = 0; q < nq; ++q) order[q] = (uint32_t)q;
-        std::vector<char> paired(nq, 0);
+        std::vector<char> taken(nq, 0);
+        auto single_cost = [&](uint32_t q) {
+            const Config &c = main_cfgs[q];
+            return (double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes);
+        };
+        // a sequence is a serial chain of columns: the longest one must not outlast the rest of a launch
+        auto chain_ok = [&](const std::vector<Q2Launch> &ls) {
+            for (const Q2Launch &L : ls) {
+                const double launch_cycles = (double)L.G * L.K * (double)ctx->local_residues /
+                                             (q2_rate(L.G, L.K, ls.size() > 1) * 0.5e9) * kSmHz;
+                const double step = 4.0 * (12.0 * L.K + 60.0);
+                if ((double)ctx->maxcols * step > 0.5 * launch_cycles) return false;
+            }
+            return true;
+        };
+        auto add_group = [&](const std::vector<uint32_t> &members, std::vector<Q2Launch> &launches) {
+            WorkItem it;
+            it.pair = true;
+            it.qa = members[0];
+            it.members = members;
+            it.launches.swap(launches);
+            for (uint32_t q : members) { taken[q] = 1; it.member_rows += ctx->q_len[q]; }
+            q2_launches += (uint32_t)it.launches.size();
+            if (it.launches.size() > 1) q2_lines = true;
+            items.push_back(std::move(it));
+        };
         if (ctx->query_pairing && nq >= 2 && ctx->ntiles) {
             std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return ctx->q_len[x] > ctx->q_len[y]; });
-            for (uint64_t i = 0; i + 1 < nq; i += 2) {
-                const uint32_t qa = order[i + 1], qb = order[i];          // qb is the longer one
-                const uint32_t m = ctx->q_len[qb];
-                const PairConfig pc = choose_pair_config(m, ctx->q2_group, ctx->q2_rows);
-                bool use = ctx->query_pairing == 2;
-                if (!use) {
-                    double single = 0;
-                    for (uint32_t q : {qa, qb}) {
-                        const Config &c = main_cfgs[q];
-                        single += (double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes);
+            // (1) two streams of long queries; the longest ones may be left to the sequence-pair kernel when that
+            // balances the lanes better
+            std::vector<uint32_t> longq;
+            for (uint32_t q : order)
+                if (ctx->q_len[q] > kMaxPassRows) longq.push_back(q);
+            if (longq.size() >= 2) {
+                double best_cost = 1e300;
+                size_t best_skip = 0;
+                std::vector<Q2Launch> best_launches;
+                const size_t max_skip = ctx->query_pairing == 2 ? 0 : std::min<size_t>(2, longq.size() - 2);
+                double skipped_cost = 0.0;
+                for (size_t skip = 0; skip <= max_skip; ++skip) {
+                    std::vector<uint32_t> lanes[2];
+                    uint64_t rows[2] = {0, 0};
+                    for (size_t i = skip; i < longq.size(); ++i) {
+                        const int l = rows[1] < rows[0] ? 1 : 0;
+                        lanes[l].push_back(longq[i]);
+                        rows[l] += ctx->q_len[longq[i]];
                     }
-                    // a sequence is a serial chain of columns: the longest one must not outlast the rest of a launch
-                    bool chain_ok = true;
-                    for (int K : pc.K) {
-                        const double launch_cycles = (double)pc.G * K * (double)ctx->local_residues /
-                                                     (q2_rate(pc.G, K, pc.passes() > 1) * 0.5e9) * kSmHz;
-                        const double step = 4.0 * (12.0 * K + 60.0);
-                        if ((double)ctx->maxcols * step > 0.5 * launch_cycles) chain_ok = false;
-                    }
-                    use = pc.cost < single && chain_ok;
+                    std::vector<Q2Launch> ls;
+                    const double c = plan_stream(lanes, ctx->q_len, ctx->q2_rows, ls) + skipped_cost;
+                    if (c < best_cost) { best_cost = c; best_skip = skip; best_launches.swap(ls); }
+                    skipped_cost += single_cost(longq[skip]);
                 }
-                if (!use) continue;
-                WorkItem it;
-                it.qa = qa; it.qb = qb; it.pair = true; it.pc = pc;
-                items.push_back(it);
-                paired[qa] = paired[qb] = 1;
-                q2_launches += pc.passes();
-                q2_max_passes = std::max(q2_max_passes, pc.passes());
-                if (pc.passes() > 1) q2_lines = true;
+                double all_single = 0.0;
+                for (uint32_t q : longq) all_single += single_cost(q);
+                if (ctx->query_pairing == 2 || (best_cost < all_single && chain_ok(best_launches))) {
+                    std::vector<uint32_t> members(longq.begin() + best_skip, longq.end());
+                    add_group(members, best_launches);
+                }
+            }
+            // (2) single-pass pairs of neighbours among the rest
+            std::vector<uint32_t> rest;
+            for (uint32_t q : order)
+                if (!taken[q] && ctx->q_len[q] <= kMaxPassRows) rest.push_back(q);
+            for (size_t i = 0; i + 1 < rest.size(); i += 2) {
+                const uint32_t qb = rest[i], qa = rest[i + 1];          // qb is the longer one
+                const PairConfig pc = choose_pair_config(ctx->q_len[qb], ctx->q2_group, ctx->q2_rows);
+                std::vector<Q2Launch> ls;
+                double cost = pc.cost;
+                if (pc.passes() == 1) {
+                    Q2Launch L;
+                    L.G = pc.G;
+                    L.K = pc.K[0];
+                    L.lane[0] = {(int32_t)qa, 0, true, true};
+                    L.lane[1] = {(int32_t)qb, 0, true, true};
+                    ls.push_back(L);
+                } else {                                                  // forced rows too few for one pass
+                    std::vector<uint32_t> lanes[2] = {{qa}, {qb}};
+                    cost = plan_stream(lanes, ctx->q_len, ctx->q2_rows, ls);
+                }
+                if (ctx->query_pairing == 2 || (cost < single_cost(qa) + single_cost(qb) && chain_ok(ls)))
+                    add_group({qa, qb}, ls);
             }
         }
         for (uint64_t q = 0; q < nq; ++q)
-            if (!paired[q]) {
+            if (!taken[q]) {
                 WorkItem it;
-                it.qa = it.qb = (uint32_t)q; it.pair = false; it.pc.G = 0; it.pc.cost = 0.0;
-                items.push_back(it);
+                it.pair = false;
+                it.qa = (uint32_t)q;
+                items.push_back(std::move(it));
             }
     }
 
+    if (ctx->verbose)
+        for (const WorkItem &it : items) {
+            if (!it.pair) {
+                const Config &c = main_cfgs[it.qa];
+                fprintf(stderr, "[swg] query %u (%u rows): sequence-pair kernel G=%d K=%d passes=%u\n", it.qa,
+                        (unsigned)ctx->q_len[it.qa], c.G, c.K, c.passes);
+                continue;
+            }
+            fprintf(stderr, "[swg] query-pair kernel, %zu queries (%llu rows), %zu launches:\n", it.members.size(),
+                    (unsigned long long)it.member_rows, it.launches.size());
+            for (const Q2Launch &L : it.launches)
+                fprintf(stderr, "[swg]   G=%d K=%d | lane 0: q %d (%u rows) from row %u%s%s | lane 1: q %d (%u rows) from row %u%s%s\n",
+                        L.G, L.K, L.lane[0].q, L.lane[0].q >= 0 ? (unsigned)ctx->q_len[L.lane[0].q] : 0u, L.lane[0].row0,
+                        L.lane[0].first ? " first" : "", L.lane[0].last ? " last" : "", L.lane[1].q,
+                        L.lane[1].q >= 0 ? (unsigned)ctx->q_len[L.lane[1].q] : 0u, L.lane[1].row0,
+                        L.lane[1].first ? " first" : "", L.lane[1].last ? " last" : "");
+        }
     SWG_CUDA(ctx, ctx->d_scores.reserve(std::max<uint64_t>(nq * n_pad, 1) * sizeof(int32_t)));
     SWG_CUDA(ctx, ctx->d_profile.reserve((size_t)max_passes * kPassBytes));
     SWG_CUDA(ctx, ctx->d_profile32.reserve((size_t)max_passes * kPassBytes));
@@ -799,10 +932,10 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     SWG_CUDA(ctx, ctx->d_resc_list.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
     const uint64_t dummy_lines = warps * 4 * (uint64_t)(kQ2MinSegCols + kQ2LineSlack);     // one per thread group (G >= 8)
     if (q2_launches) {
-        SWG_CUDA(ctx, ctx->d_profile_q2.reserve((size_t)q2_max_passes * kQ2ProfileBytes));
+        SWG_CUDA(ctx, ctx->d_profile_q2.reserve((size_t)q2_launches * kQ2ProfileBytes));
         SWG_CUDA(ctx, ctx->d_resc_list2.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
         SWG_CUDA(ctx, ctx->d_q2_counters.reserve((size_t)q2_launches * sizeof(uint32_t)));
-        if (q2_lines) SWG_CUDA(ctx, ctx->d_lines.reserve((ctx->line_units + dummy_lines) * sizeof(uint2)));
+        if (q2_lines) SWG_CUDA(ctx, ctx->d_lines.reserve((ctx->line_units + dummy_lines + 2) * sizeof(uint2)));
     }
     const TopkPlan tp = topk_plan(n_pad, top, nq);
     SWG_CUDA(ctx, ctx->d_topk_scratch.reserve(tp.scratch_keys * sizeof(uint64_t)));
@@ -864,23 +997,18 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         const WorkItem &it = items[ii];
         if (it.pair) {
             // ---- two queries per register: one launch per pass over the whole shard ----
-            const uint32_t qa = it.qa, qb = it.qb;
-            const PairConfig &pc = it.pc;
             cudaError_t e = cudaSuccess;
-            uint32_t row0 = 0;
-            for (uint32_t pass = 0; pass < pc.passes() && e == cudaSuccess; ++pass) {
-                e = launch_build_profile_q2(ctx->d_queries.as<int8_t>() + ctx->q_off[qa], ctx->q_len[qa],
-                                            ctx->d_queries.as<int8_t>() + ctx->q_off[qb], ctx->q_len[qb],
-                                            ctx->d_submat.as<int8_t>(), pc.G, pc.K[pass], row0,
-                                            ctx->d_profile_q2.as<uint8_t>() + (size_t)pass * kQ2ProfileBytes, ctx->stream);
-                row0 += (uint32_t)(pc.G * pc.K[pass]);
+            const size_t prof0 = q2_next_counter;          // profile slot = global launch number
+            auto lane_q = [&](const LaneSlice &sl) { return sl.q >= 0 ? ctx->d_queries.as<int8_t>() + ctx->q_off[sl.q] : nullptr; };
+            auto lane_m = [&](const LaneSlice &sl) { return sl.q >= 0 ? (uint32_t)ctx->q_len[sl.q] : 0u; };
+            for (size_t li = 0; li < it.launches.size() && e == cudaSuccess; ++li) {
+                const Q2Launch &L = it.launches[li];
+                e = launch_build_profile_q2(lane_q(L.lane[0]), lane_m(L.lane[0]), lane_q(L.lane[1]), lane_m(L.lane[1]),
+                                            ctx->d_submat.as<int8_t>(), L.G, L.K, L.lane[0].row0, L.lane[1].row0,
+                                            ctx->d_profile_q2.as<uint8_t>() + (prof0 + li) * kQ2ProfileBytes, ctx->stream);
                 ctx->stats.launches += 1;
             }
             WfParams pq = p;
-            pq.scores = ctx->d_scores.as<int32_t>() + (uint64_t)qa * n_pad;
-            pq.scores2 = ctx->d_scores.as<int32_t>() + (uint64_t)qb * n_pad;
-            pq.resc_count = ctx->d_counters.as<uint32_t>() + (uint64_t)qa * 4 + 3;
-            pq.resc_count2 = ctx->d_counters.as<uint32_t>() + (uint64_t)qb * 4 + 3;
             pq.resc_list = ctx->d_resc_list.as<uint32_t>();
             pq.resc_list2 = ctx->d_resc_list2.as<uint32_t>();
             pq.boundary = ctx->d_lines.as<uint2>();
@@ -889,21 +1017,48 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             pq.tile_first = 0;
             pq.tile_count = ctx->ntiles;
             pq.passes = 1;
-            for (uint32_t pass = 0; pass < pc.passes() && e == cudaSuccess; ++pass) {
-                pq.profile = ctx->d_profile_q2.as<uint8_t>() + (size_t)pass * kQ2ProfileBytes;
+            for (size_t li = 0; li < it.launches.size() && e == cudaSuccess; ++li) {
+                const Q2Launch &L = it.launches[li];
+                bool cin = false, cout = false;
+                uint32_t cin_mask = 0;
+                pq.lane_flags = 0;
+                for (int l = 0; l < 2; ++l) {
+                    const LaneSlice &sl = L.lane[l];
+                    int32_t *sc = nullptr;
+                    uint32_t *rc = nullptr;
+                    if (sl.q >= 0) {
+                        sc = ctx->d_scores.as<int32_t>() + (uint64_t)sl.q * n_pad;
+                        rc = ctx->d_counters.as<uint32_t>() + (uint64_t)sl.q * 4 + 3;
+                        pq.lane_flags |= (kLaneActive | (sl.first ? kLaneFirst : 0u)) << (2 * l);
+                        if (!sl.first) { cin = true; cin_mask |= 0xffffu << (16 * l); }
+                        if (!sl.last) cout = true;
+                    }
+                    if (l == 0) { pq.scores = sc; pq.resc_count = rc; }
+                    else { pq.scores2 = sc; pq.resc_count2 = rc; }
+                }
+                if (cin && cin_mask != 0xffffffffu) {
+                    // one lane continues, the other starts a query (or idles): its half of the lines must read as zero
+                    e = launch_clear_lane(ctx->d_lines.as<uint2>(), ctx->line_units, cin_mask, ctx->stream);
+                    ctx->stats.launches += 1;
+                    ctx->stats.stream_bytes += 2 * ctx->line_units * sizeof(uint2);
+                    if (e != cudaSuccess) break;
+                }
+                pq.profile = ctx->d_profile_q2.as<uint8_t>() + (prof0 + li) * kQ2ProfileBytes;
                 pq.task_counter = ctx->d_q2_counters.as<uint32_t>() + q2_next_counter++;
-                e = launch_q2(pc.G, pc.K[pass], pass > 0, pass + 1 < pc.passes(), grid, ctx->stream, pq);
+                e = launch_q2(L.G, L.K, cin, cout, grid, ctx->stream, pq);
                 ctx->stats.launches += 1;
                 ctx->stats.pair_launches += 1;
-                ctx->stats.stream_bytes += ctx->db_units * sizeof(uint4) +
-                                           ((pass > 0) + (pass + 1 < pc.passes())) * ctx->line_units * sizeof(uint2);
+                ctx->stats.stream_bytes += ctx->db_units * sizeof(uint4) + ((int)cin + (int)cout) * ctx->line_units * sizeof(uint2);
+                padded += 2ull * L.G * L.K * (uint64_t)((ctx->avg_cols + L.G - 1) * ctx->ntiles) * kTileSeqs;
+                // a query that ends here: its overflowed sequences are recomputed before the lane's list is reused
+                for (int l = 0; l < 2 && e == cudaSuccess; ++l)
+                    if (L.lane[l].q >= 0 && L.lane[l].last)
+                        e = recompute32((uint64_t)L.lane[l].q, l == 0 ? ctx->d_resc_list.as<uint32_t>()
+                                                                       : ctx->d_resc_list2.as<uint32_t>(), true);
             }
-            if (e == cudaSuccess) e = recompute32(qa, ctx->d_resc_list.as<uint32_t>(), true);
-            if (e == cudaSuccess) e = recompute32(qb, ctx->d_resc_list2.as<uint32_t>(), true);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "query-pair kernel launch");
             SWG_CUDA(ctx, cudaEventRecord(ctx->item_events[ii + 1], ctx->stream));
-            ctx->stats.cells += (uint64_t)(ctx->q_len[qa] + ctx->q_len[qb]) * ctx->local_residues;
-            padded += 2ull * pc.rows() * (uint64_t)((ctx->avg_cols + pc.G - 1) * ctx->ntiles) * kTileSeqs;
+            ctx->stats.cells += it.member_rows * ctx->local_residues;
             continue;
         }
         const uint64_t q = it.qa;
@@ -1021,12 +1176,9 @@ int swg_gpu_sync(swg_ctx *ctx)
             SWG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->item_events[ii], ctx->item_events[ii + 1]));
             const WorkItem &it = ctx->items[ii];
             if (!it.pair) ctx->q_seconds[it.qa] = ms * 1e-3;
-            else {
-                // a pair's time is split in proportion to the cells of its two queries
-                const double la = ctx->q_len[it.qa], lb = ctx->q_len[it.qb], sum = std::max(la + lb, 1.0);
-                ctx->q_seconds[it.qa] = ms * 1e-3 * la / sum;
-                ctx->q_seconds[it.qb] = ms * 1e-3 * lb / sum;
-            }
+            else      // a group's time is split in proportion to the cells of its queries
+                for (uint32_t q : it.members)
+                    ctx->q_seconds[q] = ms * 1e-3 * (double)ctx->q_len[q] / (double)std::max<uint64_t>(it.member_rows, 1);
         }
     }
     return SWG_OK;
@@ -1106,10 +1258,9 @@ int swg_gpu_get_query_kernels(swg_ctx *ctx, int32_t *kind, uint64_t max_queries)
     if (!ctx || !kind) return fail(ctx, SWG_ERR_ARG, "NULL argument");
     for (uint64_t q = 0; q < max_queries; ++q) kind[q] = 0;
     for (const WorkItem &it : ctx->items)
-        if (it.pair) {
-            if (it.qa < max_queries) kind[it.qa] = 1;
-            if (it.qb < max_queries) kind[it.qb] = 1;
-        }
+        if (it.pair)
+            for (uint32_t q : it.members)
+                if (q < max_queries) kind[q] = 1;
     return SWG_OK;
 }
 

@@ -75,7 +75,12 @@ struct WfParams {
     uint32_t *resc_list2;
     const uint64_t *line_off;     // [ntiles] first line of a tile inside `boundary` (uint2 units); 16 lines per tile
     uint64_t line_dummy;          // offset of the per-group dummy lines inside `boundary`
+    // the two 16-bit lanes are independent streams of queries: a lane may start a new query in a launch in which
+    // the other lane continues one
+    uint32_t lane_flags;          // kLaneActive / kLaneFirst bits, low lane in bits 0-1, high lane in bits 2-3
 };
+constexpr uint32_t kLaneActive = 1u;   // the lane holds a query: its scores are stored
+constexpr uint32_t kLaneFirst = 2u;    // ... and this launch is the query's first pass (nothing to merge with)
 
 __device__ __forceinline__ uint64_t global_seq_index(const WfParams &p, uint32_t local_seq)
 {

@@ -17,9 +17,13 @@ cudaError_t launch_build_tiles(const int8_t *d_residues, const uint64_t *d_seq_o
 cudaError_t launch_build_profile(const int8_t *d_query, uint32_t m, const int8_t *d_submat, int G, int K,
                                  uint32_t passes, uint8_t *d_profile, cudaStream_t stream);
 
-// profile.cu: one pass of the query-pair profile, [25][4096] bytes (wavefront_q2.cuh), rows row0 .. row0 + G*K - 1
+// profile.cu: the query-pair profile of one launch, [25][4096] bytes (wavefront_q2.cuh): G*K rows of each lane's query
+// starting at rowa0 / rowb0 (ma or mb = 0: the lane is idle)
 cudaError_t launch_build_profile_q2(const int8_t *d_qa, uint32_t ma, const int8_t *d_qb, uint32_t mb, const int8_t *d_submat,
-                                    int G, int K, uint32_t row0, uint8_t *d_profile, cudaStream_t stream);
+                                    int G, int K, uint32_t rowa0, uint32_t rowb0, uint8_t *d_profile, cudaStream_t stream);
+
+// profile.cu: keep only the halves selected by keep_mask (0x0000ffff or 0xffff0000) in every pass-line entry
+cudaError_t launch_clear_lane(uint2 *d_lines, uint64_t n_entries, uint32_t keep_mask, cudaStream_t stream);
 
 // topk.cu: top-r selection on 64-bit keys (score << 32 | global index), descending, all queries of a batch
 struct TopkPlan {

@@ -148,18 +148,25 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
 #pragma unroll
         for (int o = G >> 1; o > 0; o >>= 1) b = L::max2(b, __shfl_xor_sync(0xffffffffu, b, o, G));
         if (t == 0 && global_seq_index(p, lseq) < p.n_total) {
-            int s_lo = (int)(short)(b & 0xffffu), s_hi = (int)(short)(b >> 16);
-            int o_lo = 0, o_hi = 0;
-            if (CIN) { o_lo = p.scores[lseq]; o_hi = p.scores2[lseq]; }
-            s_lo = max(s_lo, o_lo);
-            s_hi = max(s_hi, o_hi);
-            p.scores[lseq] = s_lo;
-            p.scores2[lseq] = s_hi;
-            if (s_lo >= kOverflow16 && o_lo < kOverflow16) p.resc_list[atomicAdd(p.resc_count, 1u)] = lseq;
-            if (s_hi >= kOverflow16 && o_hi < kOverflow16) p.resc_list2[atomicAdd(p.resc_count2, 1u)] = lseq;
+            const int s_lo = (int)(short)(b & 0xffffu), s_hi = (int)(short)(b >> 16);
+            const uint32_t fl = p.lane_flags;
+            if (fl & kLaneActive) {
+                const int o = (fl & kLaneFirst) ? 0 : p.scores[lseq];
+                const int n = max(s_lo, o);
+                p.scores[lseq] = n;
+                if (n >= kOverflow16 && o < kOverflow16) p.resc_list[atomicAdd(p.resc_count, 1u)] = lseq;
+            }
+            if ((fl >> 2) & kLaneActive) {
+                const int o = ((fl >> 2) & kLaneFirst) ? 0 : p.scores2[lseq];
+                const int n = max(s_hi, o);
+                p.scores2[lseq] = n;
+                if (n >= kOverflow16 && o < kOverflow16) p.resc_list2[atomicAdd(p.resc_count2, 1u)] = lseq;
+            }
         }
     };
 
+    // (a lane that starts a new query while the other one continues finds zeros in its half of the lines: the host
+    // clears that half between the two launches, clear_lane_kernel)
     bool pending = false;
     uint32_t pend_lseq = 0;
     uint32_t next_task = fetch_task();

@@ -20,6 +20,7 @@ s.load_db(dl, dc)
 res = {}
 for mode in (0, 2, 1):
     s.set_option("query_pairing", mode)
+    s.set_option("verbose", 1 if mode == 1 and os.environ.get("SWG_VERBOSE") else 0)
     t0 = time.time()
     sc, keys = s.search(qc, ql, qo[:-1], b62, 10, 2, 10, want_scores=True)
     st = s.stats()
