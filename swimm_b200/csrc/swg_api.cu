@@ -815,7 +815,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     {
         std::vector<uint32_t> order(nq);
         for (uint64_t q = 0; q < nq; ++q) order[q] = (uint32_t)q;
-        std::vector<char> taken(nq, 0);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return ctx->q_len[x] > ctx->q_len[y]; });
         auto single_cost = [&](uint32_t q) {
             const Config &c = main_cfgs[q];
             return (double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes);
@@ -830,24 +830,25 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             }
             return true;
         };
-        auto add_group = [&](const std::vector<uint32_t> &members, std::vector<Q2Launch> &launches) {
-            WorkItem it;
-            it.pair = true;
-            it.qa = members[0];
-            it.members = members;
-            it.launches.swap(launches);
-            for (uint32_t q : members) { taken[q] = 1; it.member_rows += ctx->q_len[q]; }
-            q2_launches += (uint32_t)it.launches.size();
-            if (it.launches.size() > 1) q2_lines = true;
-            items.push_back(std::move(it));
-        };
-        if (ctx->query_pairing && nq >= 2 && ctx->ntiles) {
-            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return ctx->q_len[x] > ctx->q_len[y]; });
-            // (1) two streams of long queries; the longest ones may be left to the sequence-pair kernel when that
-            // balances the lanes better
+        // One candidate schedule: queries longer than `stream_above` rows go to the two streams, the others are
+        // paired with their neighbour in length.  Returns the estimated cost of the whole batch.
+        auto build = [&](uint32_t stream_above, std::vector<WorkItem> &out) -> double {
+            std::vector<char> taken(nq, 0);
+            double total = 0.0;
+            auto add_group = [&](const std::vector<uint32_t> &members, std::vector<Q2Launch> &launches, double cost) {
+                WorkItem it;
+                it.pair = true;
+                it.qa = members[0];
+                it.members = members;
+                it.launches.swap(launches);
+                for (uint32_t q : members) { taken[q] = 1; it.member_rows += ctx->q_len[q]; }
+                out.push_back(std::move(it));
+                total += cost;
+            };
+            // (1) two streams; the longest queries may be left to the sequence-pair kernel when that balances the lanes
             std::vector<uint32_t> longq;
             for (uint32_t q : order)
-                if (ctx->q_len[q] > kMaxPassRows) longq.push_back(q);
+                if (ctx->q_len[q] > stream_above) longq.push_back(q);
             if (longq.size() >= 2) {
                 double best_cost = 1e300;
                 size_t best_skip = 0;
@@ -863,21 +864,22 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                         rows[l] += ctx->q_len[longq[i]];
                     }
                     std::vector<Q2Launch> ls;
-                    const double c = plan_stream(lanes, ctx->q_len, ctx->q2_rows, ls) + skipped_cost;
-                    if (c < best_cost) { best_cost = c; best_skip = skip; best_launches.swap(ls); }
+                    const double c = plan_stream(lanes, ctx->q_len, ctx->q2_rows, ls);
+                    if (c + skipped_cost < best_cost) { best_cost = c + skipped_cost; best_skip = skip; best_launches.swap(ls); }
                     skipped_cost += single_cost(longq[skip]);
                 }
-                double all_single = 0.0;
+                double all_single = 0.0, skipped = 0.0;
                 for (uint32_t q : longq) all_single += single_cost(q);
+                for (size_t i = 0; i < best_skip; ++i) skipped += single_cost(longq[i]);
                 if (ctx->query_pairing == 2 || (best_cost < all_single && chain_ok(best_launches))) {
                     std::vector<uint32_t> members(longq.begin() + best_skip, longq.end());
-                    add_group(members, best_launches);
+                    add_group(members, best_launches, best_cost - skipped);
                 }
             }
             // (2) single-pass pairs of neighbours among the rest
             std::vector<uint32_t> rest;
             for (uint32_t q : order)
-                if (!taken[q] && ctx->q_len[q] <= kMaxPassRows) rest.push_back(q);
+                if (!taken[q] && ctx->q_len[q] <= std::min<uint32_t>(stream_above, kMaxPassRows)) rest.push_back(q);
             for (size_t i = 0; i + 1 < rest.size(); i += 2) {
                 const uint32_t qb = rest[i], qa = rest[i + 1];          // qb is the longer one
                 const PairConfig pc = choose_pair_config(ctx->q_len[qb], ctx->q2_group, ctx->q2_rows);
@@ -895,15 +897,39 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                     cost = plan_stream(lanes, ctx->q_len, ctx->q2_rows, ls);
                 }
                 if (ctx->query_pairing == 2 || (cost < single_cost(qa) + single_cost(qb) && chain_ok(ls)))
-                    add_group({qa, qb}, ls);
+                    add_group({qa, qb}, ls, cost);
             }
-        }
-        for (uint64_t q = 0; q < nq; ++q)
-            if (!taken[q]) {
+            for (uint64_t q = 0; q < nq; ++q)
+                if (!taken[q]) {
+                    WorkItem it;
+                    it.pair = false;
+                    it.qa = (uint32_t)q;
+                    out.push_back(std::move(it));
+                    total += single_cost((uint32_t)q);
+                }
+            return total;
+        };
+        if (ctx->query_pairing && nq >= 2 && ctx->ntiles) {
+            // where the streams end and the single-pass pairs begin is a planner choice too
+            double best = 1e300;
+            for (uint32_t above : {(uint32_t)kMaxPassRows, 832u, 640u, 448u, 256u}) {
+                std::vector<WorkItem> cand;
+                const double c = build(above, cand);
+                if (c < best) { best = c; items.swap(cand); }
+                if (ctx->q2_rows || ctx->q2_group) break;          // forced shapes (tests): the first candidate
+            }
+        } else {
+            for (uint64_t q = 0; q < nq; ++q) {
                 WorkItem it;
                 it.pair = false;
                 it.qa = (uint32_t)q;
                 items.push_back(std::move(it));
+            }
+        }
+        for (const WorkItem &it : items)
+            if (it.pair) {
+                q2_launches += (uint32_t)it.launches.size();
+                if (it.launches.size() > 1) q2_lines = true;
             }
     }
 
