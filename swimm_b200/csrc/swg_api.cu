@@ -816,22 +816,25 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         std::vector<uint32_t> order(nq);
         for (uint64_t q = 0; q < nq; ++q) order[q] = (uint32_t)q;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return ctx->q_len[x] > ctx->q_len[y]; });
+        // Estimated seconds of a launch: its throughput time, or the serial chain of the longest sequence when that
+        // is longer (a sequence advances one column per step of its thread group: about 24 cycles per row on a busy
+        // SM, measured on the long-sequence workload).  The same model for both kernels, so that they compare fairly.
+        const double res9 = (double)ctx->local_residues * 1e-9;
+        auto chain_seconds = [&](int K, uint32_t passes) {
+            return (double)ctx->maxcols * passes * (24.0 * K + 100.0) / kSmHz;
+        };
         auto single_cost = [&](uint32_t q) {
             const Config &c = main_cfgs[q];
-            return (double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes);
+            return std::max((double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes) * res9, chain_seconds(c.K, c.passes));
         };
-        // a sequence is a serial chain of columns: the longest one must not outlast the rest of a launch
-        auto chain_ok = [&](const std::vector<Q2Launch> &ls) {
-            for (const Q2Launch &L : ls) {
-                const double launch_cycles = (double)L.G * L.K * (double)ctx->local_residues /
-                                             (q2_rate(L.G, L.K, ls.size() > 1) * 0.5e9) * kSmHz;
-                const double step = 4.0 * (12.0 * L.K + 60.0);
-                if ((double)ctx->maxcols * step > 0.5 * launch_cycles) return false;
-            }
-            return true;
+        auto q2_cost = [&](const std::vector<Q2Launch> &ls) {
+            double t = 0.0;
+            for (const Q2Launch &L : ls)
+                t += std::max(2.0 * L.G * L.K / q2_rate(L.G, L.K, ls.size() > 1) * res9, chain_seconds(L.K, 1));
+            return t;
         };
         // One candidate schedule: queries longer than `stream_above` rows go to the two streams, the others are
-        // paired with their neighbour in length.  Returns the estimated cost of the whole batch.
+        // paired with their neighbour in length.  Returns the estimated seconds of the whole batch.
         auto build = [&](uint32_t stream_above, std::vector<WorkItem> &out) -> double {
             std::vector<char> taken(nq, 0);
             double total = 0.0;
@@ -864,14 +867,15 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                         rows[l] += ctx->q_len[longq[i]];
                     }
                     std::vector<Q2Launch> ls;
-                    const double c = plan_stream(lanes, ctx->q_len, ctx->q2_rows, ls);
+                    plan_stream(lanes, ctx->q_len, ctx->q2_rows, ls);
+                    const double c = q2_cost(ls);
                     if (c + skipped_cost < best_cost) { best_cost = c + skipped_cost; best_skip = skip; best_launches.swap(ls); }
                     skipped_cost += single_cost(longq[skip]);
                 }
                 double all_single = 0.0, skipped = 0.0;
                 for (uint32_t q : longq) all_single += single_cost(q);
                 for (size_t i = 0; i < best_skip; ++i) skipped += single_cost(longq[i]);
-                if (ctx->query_pairing == 2 || (best_cost < all_single && chain_ok(best_launches))) {
+                if (ctx->query_pairing == 2 || best_cost < all_single) {
                     std::vector<uint32_t> members(longq.begin() + best_skip, longq.end());
                     add_group(members, best_launches, best_cost - skipped);
                 }
@@ -884,7 +888,6 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 const uint32_t qb = rest[i], qa = rest[i + 1];          // qb is the longer one
                 const PairConfig pc = choose_pair_config(ctx->q_len[qb], ctx->q2_group, ctx->q2_rows);
                 std::vector<Q2Launch> ls;
-                double cost = pc.cost;
                 if (pc.passes() == 1) {
                     Q2Launch L;
                     L.G = pc.G;
@@ -894,9 +897,10 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                     ls.push_back(L);
                 } else {                                                  // forced rows too few for one pass
                     std::vector<uint32_t> lanes[2] = {{qa}, {qb}};
-                    cost = plan_stream(lanes, ctx->q_len, ctx->q2_rows, ls);
+                    plan_stream(lanes, ctx->q_len, ctx->q2_rows, ls);
                 }
-                if (ctx->query_pairing == 2 || (cost < single_cost(qa) + single_cost(qb) && chain_ok(ls)))
+                const double cost = q2_cost(ls);
+                if (ctx->query_pairing == 2 || cost < single_cost(qa) + single_cost(qb))
                     add_group({qa, qb}, ls, cost);
             }
             for (uint64_t q = 0; q < nq; ++q)
@@ -1131,7 +1135,15 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             main_tiles = first_long;
             const uint32_t long_tiles = ctx->ntiles - first_long;
             const uint64_t long_warps = (uint64_t)long_tiles * kTilePairs;          // one pair per warp at G = 32
-            int long_grid = (int)std::min<uint64_t>((long_warps + warps_per_block - 1) / warps_per_block, kMaxLongBlocks);
+            // SMs for the long tiles: in proportion to their share of the columns (the two launches run side by
+            // side, one CTA per SM), at least kMaxLongBlocks when there are that many warps of work
+            double long_cols_sum = 0.0;
+            for (uint32_t t = first_long; t < ctx->ntiles; ++t) long_cols_sum += ctx->h_tile_cols[t];
+            const double share = long_cols_sum / std::max(1.0, ctx->avg_cols * ctx->ntiles);
+            const uint64_t by_share = (uint64_t)(share * grid + 0.999);
+            int long_grid = (int)std::min<uint64_t>((long_warps + warps_per_block - 1) / warps_per_block,
+                                                    std::max<uint64_t>(kMaxLongBlocks, by_share));
+            if (long_grid > grid - 1 && main_tiles) long_grid = grid - 1;
             if (main_tiles == 0) long_grid = grid;                                    // nothing else to run
             p.profile = ctx->d_profile32.as<uint8_t>();
             p.passes = wide_cfg.passes;

@@ -24,7 +24,10 @@ def hits(stdout):
             out.append(cur)
         m = re.match(r"^(-?\d+)\t(.*)$", line)
         if m and cur is not None:
-            cur.append((int(m.group(1)), re.sub(r"[^\x20-\x7e]", "", m.group(2)).strip()))
+            # the reference may leave one garbage byte at the end of a title (sequences.c:112-116): compare the unique
+            # id embedded in the title, and the whole title only up to that byte
+            ident = re.search(r"syn\|(\d+)\|", m.group(2))
+            cur.append((int(m.group(1)), ident.group(1) if ident else re.sub(r"[^\x20-\x7e]", "", m.group(2)).strip()))
     return out
 
 
@@ -51,8 +54,16 @@ elif workload == "cfg4":
         s0 = db.offsets[t]
         L = len(q.seq(qi))
         db.residues[s0 + 11:s0 + 11 + L] = synth.mutate(rng, q.seq(qi), rate)
+elif workload == "cfg5":
+    # matrix / penalty sweep with a multi-query batch: 8 queries (ascending, one file) x the cfg1 database
+    q = synth.make_queries(np.random.default_rng(55), [61, 144, 222, 375, 567, 850, 1321, 2005])
+    db = synth.make_db(42, int(100_000 * scale) // 16 * 16, queries=q, plant_fraction=0.005)
 else:
     raise SystemExit("unknown workload " + workload)
+# (matrix, gap open, gap extend) runs; cfg5 sweeps them, the others use the defaults
+sweep = [("blosum62", "10", "2")]
+if workload == "cfg5":
+    sweep = [(m, g, e) for m in ("blosum45", "blosum80", "pam30", "pam250") for g, e in (("5", "1"), ("8", "2"), ("10", "3"), ("12", "1"))]
 with tempfile.TemporaryDirectory() as tmp:
     dbf, qf = os.path.join(tmp, "db.fasta"), os.path.join(tmp, "q.fasta")
     t0 = time.time()
@@ -65,25 +76,44 @@ with tempfile.TemporaryDirectory() as tmp:
     t0 = time.time()
     subprocess.run([OURS, "-S", "preprocess", "-i", dbf, "-o", os.path.join(tmp, "ours")], check=True, stdout=subprocess.DEVNULL)
     t_our_pre = time.time() - t0
-    same_files = all(open(os.path.join(tmp, "ref." + e), "rb").read() == open(os.path.join(tmp, "ours." + e), "rb").read()
-                     for e in ("info", "seq", "desc"))
-    print("preprocess: reference %.1f s, this repo %.1f s, files identical: %s" % (t_ref_pre, t_our_pre, same_files))
-    t0 = time.time()
-    ref = subprocess.run([REF, "-S", "search", "-q", qf, "-d", os.path.join(tmp, "ref"), "-m", "0", "-v", "32", "-c", cores, "-r", top],
-                         check=True, capture_output=True).stdout.decode("latin-1")
-    t_ref = time.time() - t0
-    t0 = time.time()
-    ours = subprocess.run([OURS, "-S", "search", "-q", qf, "-d", os.path.join(tmp, "ours"), "-m", "3", "-x", gpus, "-r", top],
-                          check=True, capture_output=True).stdout.decode("latin-1")
-    t_ours = time.time() - t0
-h_ref, h_ours = hits(ref), hits(ours)
-ok = h_ref == h_ours and len(h_ref) == q.n
-print("reference: Search time %s, %s, wall %.1f s (%s threads)" % (field(ref, "Search time:"), field(ref, "Search speed:"), t_ref, cores))
-print("this repo: Search time %s, %s, wall %.1f s (%s)" % (field(ours, "Search time:"), field(ours, "Search speed:"), t_ours, field(ours, "Execution mode:")))
-print("hit lists identical for %d queries x top %s: %s" % (len(h_ref), top, ok))
-if not ok:
-    for i, (a, b) in enumerate(zip(h_ref, h_ours)):
-        if a != b:
-            print("first difference in query", i + 1, [x for x in zip(a, b) if x[0] != x[1]][:3])
-            break
-sys.exit(0 if ok else 1)
+    same = {e: open(os.path.join(tmp, "ref." + e), "rb").read() == open(os.path.join(tmp, "ours." + e), "rb").read()
+            for e in ("info", "seq", "desc")}
+    note = ""
+    if not same["desc"]:
+        # the reference's title bug: at most one extra byte before the newline; everything else must agree
+        rl = open(os.path.join(tmp, "ref.desc"), "rb").read().split(b"\n")
+        ol = open(os.path.join(tmp, "ours.desc"), "rb").read().split(b"\n")
+        extra = sum(1 for a, b in zip(rl, ol) if a != b)
+        benign = len(rl) == len(ol) and all(a == b or (a.startswith(b) and len(a) == len(b) + 1) for a, b in zip(rl, ol))
+        note = " (.desc: %d titles carry the reference's one trailing garbage byte, sequences.c:112-116; otherwise identical: %s)" % (extra, benign)
+        same["desc"] = benign
+    same_files = all(same.values())
+    print("preprocess: reference %.1f s, this repo %.1f s, files identical: %s%s" % (t_ref_pre, t_our_pre, same_files, note))
+    all_ok = True
+    for matrix, go, ge in sweep:
+        extra = ["-s", matrix, "-g", go, "-e", ge]
+        t0 = time.time()
+        ref = subprocess.run([REF, "-S", "search", "-q", qf, "-d", os.path.join(tmp, "ref"), "-m", "0", "-v", "32", "-c", cores, "-r", top] + extra,
+                             check=True, capture_output=True).stdout.decode("latin-1")
+        t_ref = time.time() - t0
+        t0 = time.time()
+        ours = subprocess.run([OURS, "-S", "search", "-q", qf, "-d", os.path.join(tmp, "ours"), "-m", "3", "-x", gpus, "-r", top] + extra,
+                              check=True, capture_output=True).stdout.decode("latin-1")
+        t_ours = time.time() - t0
+        h_ref, h_ours = hits(ref), hits(ours)
+        ok = h_ref == h_ours and len(h_ref) == q.n
+        all_ok = all_ok and ok
+        if len(sweep) > 1:
+            print("%s -g %s -e %s: reference %s s / %s, this repo %s s / %s, best score %d, hit lists identical (%d queries x top %s): %s"
+                  % (matrix, go, ge, field(ref, "Search time:").split()[0], field(ref, "Search speed:"), field(ours, "Search time:").split()[0],
+                     field(ours, "Search speed:"), max(h[0][0] for h in h_ref if h), len(h_ref), top, ok))
+        else:
+            print("reference: Search time %s, %s, wall %.1f s (%s threads)" % (field(ref, "Search time:"), field(ref, "Search speed:"), t_ref, cores))
+            print("this repo: Search time %s, %s, wall %.1f s (%s)" % (field(ours, "Search time:"), field(ours, "Search speed:"), t_ours, field(ours, "Execution mode:")))
+            print("best score %d; hit lists identical for %d queries x top %s: %s" % (max(h[0][0] for h in h_ref if h), len(h_ref), top, ok))
+        if not ok:
+            for i, (a, b) in enumerate(zip(h_ref, h_ours)):
+                if a != b:
+                    print("first difference in query", i + 1, [x for x in zip(a, b) if x[0] != x[1]][:3])
+                    break
+sys.exit(0 if all_ok else 1)
