@@ -195,12 +195,18 @@ double shape_rate(int G, int K, uint32_t passes)
     }
 }
 
-Config choose_config(uint32_t m, double avg_cols, long force_group, long force_rows)
+Config wide_config(uint32_t m);
+
+// `residues` and `maxcols` describe the shard: on a small one the longest sequence's serial chain (one column per
+// step of its thread group, about 24 cycles per row) can outlast the throughput time, and a shape with more threads
+// per sequence (fewer rows per thread, a shorter step) wins although its saturated rate is lower.
+Config choose_config(uint32_t m, double residues, double maxcols, long force_group, long force_rows)
 {
-    (void)avg_cols;
     Config best = {32, 32, 1, false};
     if (m == 0) m = 1;
     double best_cost = 1e300;
+    const Config wide = wide_config(m);
+    const double wide_chain = maxcols * wide.passes * (24.0 * wide.K + 100.0);
     for (int G = 4; G <= 32; G *= 2) {
         if (force_group && G != force_group) continue;
         for (int K = 1; K <= kMaxRowsPerThread; ++K) {
@@ -209,7 +215,10 @@ Config choose_config(uint32_t m, double avg_cols, long force_group, long force_r
             const uint32_t passes = (m + rows - 1) / rows;
             if (passes > 1 && G != 32) continue;     // the pass boundary line is per warp: one pair per warp
             if (passes > (uint32_t)kMaxSmemPasses && !(force_group || force_rows)) continue;
-            const double c = (double)passes * rows / shape_rate(G, K, passes);
+            const double thr = (double)passes * rows / shape_rate(G, K, passes) * residues * 1e-9;
+            // (the longest tiles can be handed to the 32-thread shape, which caps the chain at that shape's)
+            const double chain = std::min(maxcols * passes * (24.0 * K + 100.0), wide_chain) / kSmHz;
+            const double c = std::max(thr, chain) + 1e-3 * thr;       // ties: the higher throughput
             if (c < best_cost) { best_cost = c; best = {G, K, passes, passes > (uint32_t)kMaxSmemPasses}; }
         }
     }
@@ -798,7 +807,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     std::vector<Config> main_cfgs(nq), wide_cfgs(nq);
     uint32_t max_passes = 1;
     for (uint64_t q = 0; q < nq; ++q) {
-        main_cfgs[q] = choose_config(ctx->q_len[q], ctx->avg_cols, ctx->force_group, ctx->force_rows);
+        main_cfgs[q] = choose_config(ctx->q_len[q], (double)ctx->local_residues, (double)ctx->maxcols, ctx->force_group, ctx->force_rows);
         wide_cfgs[q] = wide_config(ctx->q_len[q]);
         max_passes = std::max(max_passes, std::max(main_cfgs[q].passes, wide_cfgs[q].passes));
     }
@@ -1120,10 +1129,13 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             else {
                 const double total_cycles = (double)m * (double)ctx->local_residues /
                                             (shape_rate(main_cfg.G, main_cfg.K, main_cfg.passes) * 1e9) * kSmHz;
-                // cycles per column of one warp that shares its scheduler with three others
-                const double step = 4.0 * (16.0 * main_cfg.K + 60.0) * main_cfg.passes;
-                const double limit_cols = 0.35 * total_cycles / step;
-                if ((double)ctx->maxcols > 0.7 * total_cycles / step) {
+                // cycles per column of one thread group on a busy SM (about 24 per row, measured on the long-sequence
+                // workload; the same model the batch planner uses)
+                const double step = (24.0 * main_cfg.K + 100.0) * main_cfg.passes;
+                // the 32-thread shape is the less efficient one (few rows per thread): it gets only the tiles whose
+                // chain on the main shape would come close to the whole run
+                const double limit_cols = 0.8 * total_cycles / step;
+                if ((double)ctx->maxcols > 0.9 * total_cycles / step) {
                     first_long = (uint32_t)(std::upper_bound(ctx->h_tile_cols.begin(), ctx->h_tile_cols.end(),
                                                              (uint32_t)std::min(limit_cols, 4.0e9)) - ctx->h_tile_cols.begin());
                 }
