@@ -342,13 +342,14 @@ def main():
         try:
             cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_cfg2_kernels.json")))
             unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            key = "q2_single_pass" if dom is kernels.get(1) else "seqpair_q144"
+            key = "q2_middle_pass" if dom is kernels.get(1) else "seqpair_q144"
             traffic = sum(float(cap[key][k].split()[0]) * unit[cap[key][k].split()[1]]
                           for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            algo_launch = st["stream_bytes"] / max(1, st["pair_launches"]) if dom is kernels.get(1) else st["db_bytes"]
             traffic_note = ("ncu dram bytes read+written by one full-size launch (profiles/r01_ncu_full_cfg2_kernels.json, %s); "
-                            "algorithmic bytes of that launch = the tiled database, %d; a middle pass of the query-pair kernel "
-                            "also reads and writes its pass lines, 8 B per database column each way (q2_middle_pass)"
-                            % (key, st["db_bytes"]))
+                            "algorithmic bytes: the tiled database (%d) once per launch, plus -- query-pair kernel, launches that "
+                            "continue a query -- the pass lines, 8 B per database column read and 8 B written; average over "
+                            "this run's launches %.0f" % (key, st["db_bytes"], algo_launch))
         except Exception:
             pass
         roof = {"bound": "int_alu", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "GCUPS",

@@ -842,6 +842,13 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 t += std::max(2.0 * L.G * L.K / q2_rate(L.G, L.K, ls.size() > 1) * res9, chain_seconds(L.K, 1));
             return t;
         };
+        // the pass lines of multi-launch groups take 8 bytes per database column: only when that fits comfortably
+        bool lines_fit = true;
+        if (ctx->d_lines.cap < (ctx->line_units + warps * 4 * (uint64_t)(kQ2MinSegCols + kQ2LineSlack) + 2) * sizeof(uint2)) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+            lines_fit = (double)ctx->line_units * sizeof(uint2) < 0.6 * (double)free_b;
+        }
         // One candidate schedule: queries longer than `stream_above` rows go to the two streams, the others are
         // paired with their neighbour in length.  Returns the estimated seconds of the whole batch.
         auto build = [&](uint32_t stream_above, std::vector<WorkItem> &out) -> double {
@@ -861,7 +868,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             std::vector<uint32_t> longq;
             for (uint32_t q : order)
                 if (ctx->q_len[q] > stream_above) longq.push_back(q);
-            if (longq.size() >= 2) {
+            if (longq.size() >= 2 && lines_fit) {
                 double best_cost = 1e300;
                 size_t best_skip = 0;
                 std::vector<Q2Launch> best_launches;
@@ -904,9 +911,11 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                     L.lane[0] = {(int32_t)qa, 0, true, true};
                     L.lane[1] = {(int32_t)qb, 0, true, true};
                     ls.push_back(L);
-                } else {                                                  // forced rows too few for one pass
+                } else if (lines_fit) {                                   // forced rows too few for one pass
                     std::vector<uint32_t> lanes[2] = {{qa}, {qb}};
                     plan_stream(lanes, ctx->q_len, ctx->q2_rows, ls);
+                } else {
+                    continue;
                 }
                 const double cost = q2_cost(ls);
                 if (ctx->query_pairing == 2 || cost < single_cost(qa) + single_cost(qb))
@@ -971,7 +980,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     SWG_CUDA(ctx, ctx->d_resc_list.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
     const uint64_t dummy_lines = warps * 4 * (uint64_t)(kQ2MinSegCols + kQ2LineSlack);     // one per thread group (G >= 8)
     if (q2_launches) {
-        SWG_CUDA(ctx, ctx->d_profile_q2.reserve((size_t)q2_launches * kQ2ProfileBytes));
+        SWG_CUDA(ctx, ctx->d_profile_q2.reserve((size_t)kQ2ProfileBytes));
         SWG_CUDA(ctx, ctx->d_resc_list2.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
         SWG_CUDA(ctx, ctx->d_q2_counters.reserve((size_t)q2_launches * sizeof(uint32_t)));
         if (q2_lines) SWG_CUDA(ctx, ctx->d_lines.reserve((ctx->line_units + dummy_lines + 2) * sizeof(uint2)));
@@ -1037,16 +1046,8 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         if (it.pair) {
             // ---- two queries per register: one launch per pass over the whole shard ----
             cudaError_t e = cudaSuccess;
-            const size_t prof0 = q2_next_counter;          // profile slot = global launch number
             auto lane_q = [&](const LaneSlice &sl) { return sl.q >= 0 ? ctx->d_queries.as<int8_t>() + ctx->q_off[sl.q] : nullptr; };
             auto lane_m = [&](const LaneSlice &sl) { return sl.q >= 0 ? (uint32_t)ctx->q_len[sl.q] : 0u; };
-            for (size_t li = 0; li < it.launches.size() && e == cudaSuccess; ++li) {
-                const Q2Launch &L = it.launches[li];
-                e = launch_build_profile_q2(lane_q(L.lane[0]), lane_m(L.lane[0]), lane_q(L.lane[1]), lane_m(L.lane[1]),
-                                            ctx->d_submat.as<int8_t>(), L.G, L.K, L.lane[0].row0, L.lane[1].row0,
-                                            ctx->d_profile_q2.as<uint8_t>() + (prof0 + li) * kQ2ProfileBytes, ctx->stream);
-                ctx->stats.launches += 1;
-            }
             WfParams pq = p;
             pq.resc_list = ctx->d_resc_list.as<uint32_t>();
             pq.resc_list2 = ctx->d_resc_list2.as<uint32_t>();
@@ -1082,7 +1083,13 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                     ctx->stats.stream_bytes += 2 * ctx->line_units * sizeof(uint2);
                     if (e != cudaSuccess) break;
                 }
-                pq.profile = ctx->d_profile_q2.as<uint8_t>() + (prof0 + li) * kQ2ProfileBytes;
+                // the launch's profile (one slot: the stream orders the build behind the previous launch, 100 KB, ~5 us)
+                e = launch_build_profile_q2(lane_q(L.lane[0]), lane_m(L.lane[0]), lane_q(L.lane[1]), lane_m(L.lane[1]),
+                                            ctx->d_submat.as<int8_t>(), L.G, L.K, L.lane[0].row0, L.lane[1].row0,
+                                            ctx->d_profile_q2.as<uint8_t>(), ctx->stream);
+                ctx->stats.launches += 1;
+                if (e != cudaSuccess) break;
+                pq.profile = ctx->d_profile_q2.as<uint8_t>();
                 pq.task_counter = ctx->d_q2_counters.as<uint32_t>() + q2_next_counter++;
                 e = launch_q2(L.G, L.K, cin, cout, grid, ctx->stream, pq);
                 ctx->stats.launches += 1;

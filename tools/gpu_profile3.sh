@@ -12,7 +12,7 @@ fi
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-pipebench"
 $CMD > gpurun_out/prof3_plain.json 2> gpurun_out/prof3_plain.err || exit 1
 i=0
-for pat in "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.0, .bool.0" "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.1, .bool.1" "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.1, .bool.0" "wavefront_kernel<swg::Lane16, .int.8, "; do
+for pat in "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.0, .bool.1" "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.1, .bool.1" "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.1, .bool.0" "wavefront_kernel<swg::Lane16, .int.8, "; do
   i=$((i+1))
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"$pat" -s 1 -c 1 -o gpurun_out/prof3_$i $CMD > gpurun_out/ncu3_$i.log 2>&1
   echo "capture $i exit $?"

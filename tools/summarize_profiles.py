@@ -39,7 +39,7 @@ keys = ["gpu__time_duration.sum", "sm__inst_executed_pipe_alu.avg.pct_of_peak_su
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
 res = {}
 keys += ["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
-for i, name in [(1, "q2_single_pass"), (2, "q2_middle_pass"), (3, "q2_last_pass"), (4, "seqpair_q144")]:
+for i, name in [(1, "q2_first_pass"), (2, "q2_middle_pass"), (3, "q2_last_pass"), (4, "seqpair_q144")]:
     rep = os.path.join(G, "prof3_%d.ncu-rep" % i)
     if not os.path.exists(rep):
         continue
