@@ -86,6 +86,35 @@ def test_pairs_many_tasks_per_warp(gpu, oracle, forced, blocks, shape):
     assert np.array_equal(got, want), np.argwhere(got != want)[:8]
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_streams_random_batches(gpu, oracle, seed):
+    """The two lanes as streams: batches of 5 to 11 queries of random lengths (1 ... 3000 rows, duplicates and
+    zero-length included), so that queries start and end in either lane at unrelated launches -- fresh lane next to a
+    continuing one (cleared line halves), idle lane tails, scores merged over several launches.  Planner's own choice
+    of launch heights and of the stream threshold; one CTA for two of the seeds (dozens of sequences per thread group)."""
+    rng = np.random.default_rng(700 + seed)
+    n = int(rng.integers(5, 12))
+    qlens = sorted(int(x) for x in np.concatenate([rng.integers(1, 3000, n - 2), [1100, 1100]]))
+    qc, ql, qo, dc, dl, do = _random_case(800 + seed, 320, qlens, mu=4.6, sigma=0.8, hi=1500, plant=0.15)
+    if seed == 4:                                   # a zero-length query in the batch
+        ql = np.concatenate([[0], ql]).astype(np.uint16)
+        qo = np.concatenate([[0], qo]).astype(np.uint32)
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    gpu.load_db(dl, dc)
+    gpu.set_option("grid_blocks", 1 if seed % 2 else 0)
+    try:
+        got, keys = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 5, want_scores=True)
+        kinds = gpu.query_kernels()
+    finally:
+        gpu.set_option("grid_blocks", 0)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:8]
+    assert kinds.sum() >= len(ql) - 1               # everything but at most one query ran the query-pair kernel
+    for qi in range(len(ql)):
+        ts, ti = oracle.top(want[qi], 5)
+        ks, ki = _keys_to_order(keys[qi])
+        assert np.array_equal(ki, ti.astype(np.int64)) and np.array_equal(ks, ts)
+
+
 def test_planner_shapes_vs_oracle(gpu, oracle):
     """The shapes the planner itself picks for the benchmark's query lengths (scaled-down database)."""
     qlens = [144, 189, 222, 375, 464, 567, 657, 729, 850, 1000, 1500, 2005]
