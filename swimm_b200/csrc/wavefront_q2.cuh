@@ -7,20 +7,24 @@
 //     packs the scores of two database letters disappears.  Per cell pair: 3.5 ALU-pipe instructions
 //     (VIMNMX3.RELU, 2 x VIADDMNMX, VIMNMX3 / 2) + 2 VIADD.16x2 on the FMA-heavy pipe, against 4.5 + 2
 //     (pipebench: mix_q2_3p5alu_2viadd_immediate vs mix_v2_immediate_penalties);
-//   * the profile is 4 bytes per (row, letter): 25 letters x 4 KB = 100 KB for the 1024 rows of a pass, so a
-//     CTA keeps ONE pass in shared memory and a query pair longer than G*K rows is searched PASS BY PASS, one
-//     launch per pass over the whole database.  The last row (H, F) of a pass is parked in a per-sequence
-//     line in HBM (8 bytes per database column, written once and read once by the next launch: ~60 GB/s on the
-//     Swiss-Prot-sized benchmark, 1 % of the HBM roofline);
+//   * the profile is 4 bytes per (row, letter): 25 letters x 4 KB = 100 KB for 1024 rows, so a CTA keeps the rows of
+//     ONE launch in shared memory and longer queries are searched PASS BY PASS, one launch per pass over the whole
+//     shard.  The last row (H, F) of a pass is parked in a per-sequence line in HBM (8 bytes per database column,
+//     written once and read once by the next launch: ~70 GB/s on the Swiss-Prot-sized benchmark, 1 % of the HBM
+//     roofline);
+//   * the two lanes are INDEPENDENT STREAMS of queries (swg_api.cu, plan_stream): a launch computes G*K rows of each
+//     lane's current query, launch boundaries fall where a query ends, and a lane may start its next query while the
+//     other continues one.  Per lane and launch: whether the rows continue from the line (the host clears the half of
+//     a lane that starts fresh), whether the score is merged with the stored one, whether the lane is idle;
 //   * a group of G threads owns ONE database sequence (the half of a tile pair is picked by the PRMT selector
-//     that builds the column word), so groups of 8 and 16 threads can run multi-pass queries too.
+//     that builds the column word).  Groups of 8 and 16 threads serve single-launch pairs of short queries.
 //
 // Exactness is unchanged: wrapping 16-bit lanes, a lane (= query) whose running best reaches kOverflow16 in any
-// pass is listed once and recomputed by the 32-bit kernel of wavefront.cuh.
+// launch is listed once and recomputed by the 32-bit kernel of wavefront.cuh when the query ends.
 //
-// Used by swg_gpu_run() for batches of at least two queries (queries of similar length are paired); a single
-// query runs the sequence-pair kernel.  Role in the reference: the same cpu_search_avx2_sp task loop
-// (CPUsearch.c:482-548), which also walks Qcount x groups tasks.
+// Used by swg_gpu_run() for batches of at least two queries; a single query runs the sequence-pair kernel.  Role
+// in the reference: the same cpu_search_avx2_sp task loop (CPUsearch.c:482-548), which also walks Qcount x groups
+// tasks.
 #pragma once
 
 #include <type_traits>
@@ -29,8 +33,8 @@
 
 namespace swg {
 
-// G threads x K rows (K a multiple of 4); CIN: the rows above come from the line of the previous pass;
-// COUT: the last row is parked for the next pass; GOE/GE > 0: gap penalties as immediates.
+// G threads x K rows (K even); CIN: a lane's rows continue from the line of the previous launch; COUT: the last
+// row is parked for the next launch; GOE/GE > 0: gap penalties as immediates.
 template <int G, int K, bool CIN, bool COUT, int GOE, int GE>
 __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const WfParams p)
 {
