@@ -112,6 +112,13 @@ int swg_gpu_get_query_seconds(swg_ctx *ctx, double *seconds, uint64_t max_querie
  * (one query, two database sequences per register), 1 = query-pair kernel (two queries of a batch per register) */
 int swg_gpu_get_query_kernels(swg_ctx *ctx, int32_t *kind, uint64_t max_queries);
 
+/* The schedule swg_gpu_run would use for a batch of queries with these lengths on a shard of n_sequences sequences /
+ * n_residues residues whose longest sequence has longest_sequence residues, as text (one line per query or launch,
+ * the format of option "verbose").  Pure host code: works without a GPU.  query_pairing as the option (0/1/2).
+ * At most capacity - 1 characters are written (NUL-terminated); returns SWG_OK or SWG_ERR_ARG. */
+int swg_plan_describe(const uint16_t *q_lengths, uint64_t q_count, uint64_t n_sequences, uint64_t n_residues,
+                      uint32_t longest_sequence, int query_pairing, char *text, uint64_t capacity);
+
 /* Measured issue rates of the search kernel's instruction mix (the integer roofline the search is
  * reported against).  ginstr_per_s[p] = 1e9 thread-instructions per second on the whole GPU for probe p,
  * sm_mhz[p] = the SM clock during it, names[p] = static strings.  max_probes >= 32 is enough. */

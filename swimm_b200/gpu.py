@@ -18,7 +18,7 @@ ABI_SYMBOLS = [
     "swg_gpu_device_count", "swg_gpu_create", "swg_gpu_destroy", "swg_gpu_last_error", "swg_gpu_load_db",
     "swg_gpu_load_db_shard", "swg_gpu_load_db_interleaved", "swg_gpu_db_local_sequences", "swg_gpu_db_local_residues", "swg_gpu_search",
     "swg_gpu_set_queries", "swg_gpu_run", "swg_gpu_fetch", "swg_gpu_sync", "swg_gpu_get_stats", "swg_gpu_get_query_seconds",
-    "swg_gpu_get_query_kernels", "swg_gpu_pipebench",
+    "swg_gpu_get_query_kernels", "swg_plan_describe", "swg_gpu_pipebench",
     "swg_gpu_set_option", "swg_gpu_debug_read", "swimm_gpu_search_avx2_compat",
 ]
 
@@ -70,6 +70,7 @@ def load_library() -> C.CDLL:
     L.swg_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.swg_gpu_get_query_seconds.argtypes = [vp, vp, u64]
     L.swg_gpu_get_query_kernels.argtypes = [vp, vp, u64]
+    L.swg_plan_describe.argtypes = [vp, u64, u64, u64, C.c_uint32, i32, C.c_char_p, u64]
     L.swg_gpu_pipebench.argtypes = [vp, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.swg_gpu_debug_read.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     L.swg_gpu_set_option.argtypes = [vp, C.c_char_p, C.c_long]
@@ -100,6 +101,17 @@ def merge_top_keys(parts: list[np.ndarray], top: int) -> np.ndarray:
     allk = np.concatenate(parts, axis=1)
     allk = -np.sort(-allk.astype(np.int64), axis=1)      # keys are < 2^63 (scores are non-negative int32)
     return allk[:, :top].astype(np.uint64)
+
+
+def plan_describe(q_lengths, n_sequences: int, n_residues: int, longest_sequence: int, query_pairing: int = 1) -> str:
+    """The schedule the library would use for a batch (host-only: works without a GPU)."""
+    L = load_library()
+    ql = np.ascontiguousarray(q_lengths, dtype=np.uint16)
+    buf = C.create_string_buffer(1 << 20)
+    st = L.swg_plan_describe(ql.ctypes.data, len(ql), n_sequences, n_residues, longest_sequence, query_pairing, buf, len(buf))
+    if st != 0:
+        raise SwgError("swg_plan_describe -> %d: %s" % (st, L.swg_gpu_last_error(None).decode()))
+    return buf.value.decode()
 
 
 class GpuSearch:

@@ -14,7 +14,7 @@ from tests.helpers import GOLDEN, ROOT
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "swimm_gpu.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(sw(?:g|imm)_gpu_\w+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(sw(?:g|imm)_(?:gpu|plan)_\w+)\s*\(", hdr))
     assert declared == set(gpu.ABI_SYMBOLS), declared ^ set(gpu.ABI_SYMBOLS)
     L = C.CDLL(gpu.LIB_PATH)
     for name in declared:
