@@ -1,6 +1,6 @@
 """Full-size cross-check on the GPU box: ALL scores of a workload computed three ways -- the sequence-pair kernel
 only (query_pairing = 0), the query-pair kernel for every pair (2) and the planner's mix (1) -- must be identical
-(two independent implementations of the recurrence, 11.4 M scores on cfg2).  Usage: python tools/full_crosscheck.py [scale]"""
+(two independent implementations of the recurrence, 11.4 M scores on cfg2).  Usage: python tools/full_crosscheck.py [scale] [cfg2|cfg3]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,8 +8,12 @@ import numpy as np
 from swimm_b200 import gpu, host, synth
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+workload = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
 q = synth.make_queries(np.random.default_rng(7), synth.QUERY_LENGTHS)
-db = synth.make_db(1000, int(570_000 * scale) // 16 * 16, mu=5.675, queries=q)
+if workload == "cfg3":
+    db = synth.make_db(3, int(6_000_000 * scale) // 16 * 16, mu=5.2, sigma=0.6, queries=q)
+else:
+    db = synth.make_db(1000, int(570_000 * scale) // 16 * 16, mu=5.675, queries=q)
 _, dl, dc = synth.length_sorted(db)
 _, ql, qc = synth.length_sorted(q)
 qo = np.zeros(q.n + 1, np.uint32)
@@ -18,7 +22,8 @@ b62 = host.submat("blosum62")
 s = gpu.GpuSearch(0)
 s.load_db(dl, dc)
 res = {}
-for mode in (0, 2, 1):
+print("%s: %d sequences, %d residues" % (workload, len(dl), len(dc)), flush=True)
+for mode in ((0, 1) if workload == "cfg3" else (0, 2, 1)):
     s.set_option("query_pairing", mode)
     s.set_option("verbose", 1 if mode == 1 and os.environ.get("SWG_VERBOSE") else 0)
     t0 = time.time()
@@ -29,7 +34,7 @@ for mode in (0, 2, 1):
           % (mode, int(s.query_kernels().sum()), st["launches"], st["search_seconds"], st["cells"] / st["search_seconds"] / 1e9,
              int(sc.max()), int(sc.astype(np.int64).sum())))
 ok = True
-for mode in (2, 1):
+for mode in ((1,) if workload == "cfg3" else (2, 1)):
     same_s = np.array_equal(res[0][0], res[mode][0])
     same_k = np.array_equal(res[0][1], res[mode][1])
     print("query_pairing=%d vs 0: %d x %d scores identical: %s, top-10 keys identical: %s (%d differing scores)"
