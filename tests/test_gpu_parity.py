@@ -286,6 +286,39 @@ def test_cli_search_prints_the_reference_hit_lists(tmp_path, name):
     assert "Search speed:" in out and "Execution mode:\t\t\tB200 GPU only (1 GPU" in out
 
 
+def test_cli_several_query_files_against_the_resident_database(tmp_path):
+    """`-q a.fasta,b.fasta`: the database is uploaded once, every file gets its own report, and each report's hit
+    lists equal the ones of a separate run (and therefore the reference's)."""
+    import json
+    import os
+    import re
+    import subprocess
+    from tests.helpers import GOLDEN, ROOT
+    exe = os.path.join(ROOT, "swimm_b200", "swimm")
+    prefix = str(tmp_path / "db")
+    subprocess.run([exe, "-S", "preprocess", "-i", os.path.join(GOLDEN, "basic.db.fasta"), "-o", prefix], check=True,
+                   stdout=subprocess.DEVNULL)
+    meta = json.load(open(os.path.join(GOLDEN, "basic.json")))
+    run = meta["runs"][0]
+    qa, qb = os.path.join(GOLDEN, "basic.q.fasta"), os.path.join(GOLDEN, "edge.q.fasta")
+    common = ["-d", prefix, "-m", "3", "-r", str(meta["n"]), "-s", run["matrix"], "-g", str(run["go"]), "-e", str(run["ge"])]
+
+    def reports(files):
+        out = subprocess.run([exe, "-S", "search", "-q", files] + common, check=True, capture_output=True, text=True).stdout
+        parts = out.split("Query filename:")[1:]
+        res = []
+        for part in parts:
+            hits = [[int(m.group(1)), int(m.group(2))] for m in re.finditer(r"^(-?\d+)\t.*syn\|(\d+)\|", part, re.M)]
+            res.append((part.split("\n")[0].strip(), part.count("Query no."), hits))
+        return res
+
+    both = reports(qa + "," + qb)
+    assert [r[0] for r in both] == [qa, qb]
+    assert both[0] == reports(qa)[0] and both[1] == reports(qb)[0]
+    flat = [h for q in run["hits"] for h in q]
+    assert both[0][2] == flat                                   # the first file: the reference's own printed lists
+
+
 def test_full_sort_path_top_larger_than_select_limit(gpu, oracle):
     """`-r <n>` with n > 2048: the bitonic full sort instead of the selection kernels."""
     qc, ql, qo, dc, dl, do = _random_case(17, 5000, [64], mu=3.8, sigma=0.5, hi=200, plant=0.02)
