@@ -378,7 +378,7 @@ def main():
                                    "BLOSUM62, gap 10/2, top %d" % (args.workload, q.n, int(ql.min()), int(ql.max()), q_res,
                                                                     n_local, len(dc), TOP),
                        "sharding": "tile round-robin, one shard per GPU, hit lists merged per step",
-                       "l2": "tiled database per GPU (%d MB) exceeds the 126 MB L2; every query streams it once"
+                       "l2": "tiled database per GPU (%d MB) exceeds the 126 MB L2; every search launch streams it once"
                              % (st["db_bytes"] >> 20)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
             "roofline": roof, "cpu_baseline": cpu_base,
