@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <set>
 #include <vector>
 
 #include "../../include/swimm_gpu.h"
@@ -87,6 +88,7 @@ struct swg_ctx {
     std::vector<uint32_t> h_counters;
     std::vector<cudaEvent_t> q_events;      // q_count + 1 marks around every query's kernels
     std::vector<double> q_seconds;
+    std::vector<uint32_t> warmed;           // kernel instantiations already loaded on this device (see warm_kernels)
     uint64_t run_top = 0, run_top_stride = 0;
     bool run_done = false, run_kept_scores = false;
 
@@ -650,6 +652,54 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     const TopkPlan tp = topk_plan(n_pad, top, nq);
     SWG_CUDA(ctx, ctx->d_topk_scratch.reserve(tp.scratch_keys * sizeof(uint64_t)));
     SWG_CUDA(ctx, ctx->d_top_out.reserve(std::max<uint64_t>(nq * top, 1) * sizeof(uint64_t)));
+
+    // The CUDA runtime loads a kernel's code the first time it is launched (a millisecond or two per instantiation,
+    // and a batch may use a dozen shapes).  Every instantiation this run needs and this context has not launched yet
+    // is launched once on an empty task list BEFORE the timed region, so that the reported search time is the search.
+    {
+        WfParams w;
+        memset(&w, 0, sizeof(w));
+        w.gap_open_extend = ctx->open_gap + ctx->extend_gap;
+        w.gap_extend = ctx->extend_gap;
+        w.task_counter = ctx->d_counters.as<uint32_t>();        // incremented by the empty launches, zeroed again below
+        w.resc_count = ctx->d_counters.as<uint32_t>() + 1;      // stays 0: "nothing to recompute"
+        w.resc_count2 = ctx->d_counters.as<uint32_t>() + 1;
+        w.passes = 1;
+        cudaError_t we = cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(uint32_t), ctx->stream);
+        const uint32_t fast = (w.gap_open_extend == kFastGapOpenExtend && w.gap_extend == kFastGapExtend) ? 1u : 0u;
+        auto fresh = [&](uint32_t key) {
+            key = key * 2 + fast;
+            if (std::find(ctx->warmed.begin(), ctx->warmed.end(), key) != ctx->warmed.end()) return false;
+            ctx->warmed.push_back(key);
+            return true;
+        };
+        auto warm_seqpair = [&](bool lane32, const Config &c) {
+            w.profile = lane32 ? ctx->d_profile32.as<uint8_t>() : ctx->d_profile.as<uint8_t>();
+            w.passes = c.passes;
+            const uint32_t key = ((((lane32 ? 1u : 0u) * 64 + (uint32_t)c.G) * 64 + (uint32_t)c.K) * 4 + (c.passes > 1 ? 1u : 0u) +
+                                  (c.global_profile ? 2u : 0u));
+            if (we == cudaSuccess && fresh(key)) we = launch_wavefront(lane32, c, 1, ctx->stream, w);
+        };
+        for (const WorkItem &it : items) {
+            if (!ctx->ntiles) break;
+            if (!it.pair) {
+                warm_seqpair(false, main_cfgs[it.qa]);
+                warm_seqpair(false, wide_cfgs[it.qa]);
+                warm_seqpair(true, wide_cfgs[it.qa]);
+                continue;
+            }
+            for (uint32_t q : it.members) warm_seqpair(true, wide_cfgs[q]);
+            w.profile = ctx->d_profile_q2.as<uint8_t>();
+            for (const Q2Launch &L : it.launches) {
+                bool cin = false, cout = false;
+                for (int l = 0; l < 2; ++l)
+                    if (L.lane[l].q >= 0) { cin |= !L.lane[l].first; cout |= !L.lane[l].last; }
+                const uint32_t key = (1u << 20) + (((uint32_t)L.G * 64 + (uint32_t)L.K) * 4 + (cin ? 1u : 0u) + (cout ? 2u : 0u));
+                if (we == cudaSuccess && fresh(key)) we = launch_q2(L.G, L.K, cin, cout, 1, ctx->stream, w);
+            }
+        }
+        if (we != cudaSuccess) return cuda_fail(ctx, we, "kernel warm-up");
+    }
 
     SWG_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t), ctx->stream));
