@@ -131,7 +131,10 @@ int swg_gpu_debug_read(swg_ctx *ctx, const char *name, void *out, uint64_t max_b
 
 /* tuning knobs (all optional): name in {"long_threshold", "force_group", "force_rows", "block_threads",
  * "query_pairing" (0 never / 1 planner / 2 always pair the queries of a batch for the query-pair kernel),
- * "q2_group", "q2_rows" (forced shape of the query-pair kernel), "grid_blocks" (CTAs per search launch, 0 = one per SM)} */
+ * "q2_group", "q2_rows" (forced shape of the query-pair kernel), "grid_blocks" (CTAs per search launch, 0 = one per SM),
+ * "pass_lines" (1 default; 0 = never allocate the query-pair kernel's pass lines, 8 bytes per database column:
+ * only single-launch pairs are formed, longer queries run the sequence-pair kernel), "verbose" (1 = print every
+ * run's schedule to stderr)} */
 int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value);
 
 /* Drop-in with the reference signature (CPUsearch.h:37-39).  n_threads is read as the number of GPUs

@@ -98,6 +98,7 @@ struct swg_ctx {
     long query_pairing = 1;                 // 0: never pair queries, 1: pair when the planner expects a gain, 2: always
     long q2_group = 0, q2_rows = 0;         // forced shape of the query-pair kernel (0: planner)
     long verbose = 0;                       // 1: print the schedule of every run to stderr
+    long pass_lines = 1;                    // 0: never allocate pass lines (8 B per database column): single-launch pairs only
     long grid_blocks = 0;                   // CTAs per search launch (0: one per SM); small values make every warp run many tasks
 
     swg_stats stats;
@@ -365,6 +366,9 @@ int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value)
         if (value < 0 || value > kMaxRowsPerThread || value % 2 || (value > 0 && value < 8))
             return fail(ctx, SWG_ERR_ARG, "q2_rows must be 0 or an even number in 8..32");
         ctx->q2_rows = value;
+    } else if (!strcmp(name, "pass_lines")) {
+        if (value != 0 && value != 1) return fail(ctx, SWG_ERR_ARG, "pass_lines must be 0 or 1");
+        ctx->pass_lines = value;
     } else if (!strcmp(name, "verbose")) {
         ctx->verbose = value;
     } else if (!strcmp(name, "grid_blocks")) {
@@ -606,8 +610,8 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     const int warps_per_block = kBlockThreads / 32;
     const size_t warps = (size_t)grid * warps_per_block;
     // the pass lines of multi-launch groups take 8 bytes per database column: only when that fits comfortably
-    bool lines_fit = true;
-    if (ctx->d_lines.cap < (ctx->line_units + warps * 4 * (uint64_t)(kQ2MinSegCols + kQ2LineSlack) + 2) * sizeof(uint2)) {
+    bool lines_fit = ctx->pass_lines != 0;
+    if (lines_fit && ctx->d_lines.cap < (ctx->line_units + warps * 4 * (uint64_t)(kQ2MinSegCols + kQ2LineSlack) + 2) * sizeof(uint2)) {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
         lines_fit = (double)ctx->line_units * sizeof(uint2) < 0.6 * (double)free_b;
@@ -625,15 +629,27 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     opts.force_rows = ctx->force_rows;
     std::vector<Config> main_cfgs, wide_cfgs;
     std::vector<WorkItem> &items = ctx->items;
-    plan_batch(ctx->q_len, shape, opts, main_cfgs, wide_cfgs, items);
     uint32_t max_passes = 1, q2_launches = 0;
     bool q2_lines = false;
-    for (uint64_t q = 0; q < nq; ++q) max_passes = std::max(max_passes, std::max(main_cfgs[q].passes, wide_cfgs[q].passes));
-    for (const WorkItem &it : items)
-        if (it.pair) {
-            q2_launches += (uint32_t)it.launches.size();
-            if (it.launches.size() > 1) q2_lines = true;
-        }
+    const uint64_t dummy_lines = warps * 4 * (uint64_t)(kQ2MinSegCols + kQ2LineSlack);     // one per thread group (G >= 8)
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        plan_batch(ctx->q_len, shape, opts, main_cfgs, wide_cfgs, items);
+        max_passes = 1;
+        q2_launches = 0;
+        q2_lines = false;
+        for (uint64_t q = 0; q < nq; ++q) max_passes = std::max(max_passes, std::max(main_cfgs[q].passes, wide_cfgs[q].passes));
+        for (const WorkItem &it : items)
+            if (it.pair) {
+                q2_launches += (uint32_t)it.launches.size();
+                if (it.launches.size() > 1) q2_lines = true;
+            }
+        if (!q2_lines) break;
+        const cudaError_t le = ctx->d_lines.reserve((ctx->line_units + dummy_lines + 2) * sizeof(uint2));
+        if (le == cudaSuccess) break;
+        if (le != cudaErrorMemoryAllocation || attempt == 1) return cuda_fail(ctx, le, "pass lines");
+        cudaGetLastError();              // not enough memory for the pass lines after all: plan again without them
+        shape.lines_fit = false;
+    }
     if (ctx->verbose) fputs(describe_plan(ctx->q_len, main_cfgs, items).c_str(), stderr);
 
     SWG_CUDA(ctx, ctx->d_scores.reserve(std::max<uint64_t>(nq * n_pad, 1) * sizeof(int32_t)));
@@ -642,12 +658,10 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     SWG_CUDA(ctx, ctx->d_boundary.reserve(2 * warps * (size_t)(ctx->maxcols + kBoundarySlack) * sizeof(uint2)));
     SWG_CUDA(ctx, ctx->d_counters.reserve(std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t)));
     SWG_CUDA(ctx, ctx->d_resc_list.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
-    const uint64_t dummy_lines = warps * 4 * (uint64_t)(kQ2MinSegCols + kQ2LineSlack);     // one per thread group (G >= 8)
     if (q2_launches) {
         SWG_CUDA(ctx, ctx->d_profile_q2.reserve((size_t)kQ2ProfileBytes));
         SWG_CUDA(ctx, ctx->d_resc_list2.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
         SWG_CUDA(ctx, ctx->d_q2_counters.reserve((size_t)q2_launches * sizeof(uint32_t)));
-        if (q2_lines) SWG_CUDA(ctx, ctx->d_lines.reserve((ctx->line_units + dummy_lines + 2) * sizeof(uint2)));
     }
     const TopkPlan tp = topk_plan(n_pad, top, nq);
     SWG_CUDA(ctx, ctx->d_topk_scratch.reserve(tp.scratch_keys * sizeof(uint64_t)));

@@ -213,6 +213,23 @@ def test_pairs_equal_single_query_path_at_scale(gpu):
     assert paired.max() > 100          # the planted homologs are there
 
 
+def test_without_pass_lines_only_single_launch_pairs(gpu, oracle):
+    """`pass_lines` = 0 (or not enough device memory for 8 bytes per database column): queries longer than one pass
+    fall back to the sequence-pair kernel, the short ones are still paired; same scores."""
+    qc, ql, qo, dc, dl, do = _random_case(77, 300, [100, 130, 600, 640, 1500, 2600])
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    gpu.load_db(dl, dc)
+    gpu.set_option("pass_lines", 0)
+    try:
+        got, _ = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 0, want_scores=True)
+        kinds = gpu.query_kernels()
+        st = gpu.stats()
+    finally:
+        gpu.set_option("pass_lines", 1)
+    assert np.array_equal(got, want)
+    assert list(kinds) == [1, 1, 1, 1, 0, 0] and st["pair_launches"] == 2
+
+
 def test_pairs_degenerate_inputs(gpu):
     b62 = host.submat("blosum62")
     # two queries of one residue against one sequence of one residue
