@@ -14,7 +14,9 @@ $CMD > gpurun_out/prof3_plain.json 2> gpurun_out/prof3_plain.err || exit 1
 i=0
 for pat in "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.0, .bool.1" "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.1, .bool.1" "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.1, .bool.0" "wavefront_kernel<swg::Lane16, .int.8, "; do
   i=$((i+1))
-  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"$pat" -s 1 -c 1 -o gpurun_out/prof3_$i $CMD > gpurun_out/ncu3_$i.log 2>&1
+  if [ -n "$ONLY" ] && [ "$ONLY" != "$i" ] && [ "$ONLY" != "23" -o $i -lt 2 -o $i -gt 3 ]; then continue; fi
+  # the first launches of every instantiation are the empty warm-up launches of the first run: skip past them
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"$pat" -s 10 -c 1 -f -o gpurun_out/prof3_$i $CMD > gpurun_out/ncu3_$i.log 2>&1
   echo "capture $i exit $?"
 done
 ls -la gpurun_out | grep prof3
