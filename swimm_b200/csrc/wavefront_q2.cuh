@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
     reg out_h = L::splat(0), out_f = L::splat(0);
     uint32_t pk = pad_pk;
     const uint32_t slice_off = (uint32_t)t * 16;
+    uint32_t first_mask = t == 0 ? 0xffffffffu : 0u;            // all ones in the thread that feeds the pipeline
+    asm volatile("" : "+r"(first_mask));                         // opaque: keeps the blends below from turning back into selects
 
     // One step: process the column whose word arrived in the previous step with the (H, F) of the row above handed
     // down now, and form DS for the column whose word arrives now (see wavefront.cuh).  HEAD steps (the first G of
@@ -96,11 +98,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
         uint32_t pkn = __shfl_up_sync(0xffffffffu, pk, 1, G);
         reg r_h = __shfl_up_sync(0xffffffffu, out_h, 1, G);
         reg r_f = __shfl_up_sync(0xffffffffu, out_f, 1, G);
-        if (t == 0) {
-            pkn = in_pkn;
-            r_h = CIN ? in_hf.x : L::splat(0);
-            r_f = CIN ? in_hf.y : L::splat(0);
-        }
+        // thread 0 takes the entering column word and the (H, F) above row 0 instead: a mask blend (one LOP3 each,
+        // no predicate to keep alive across the row loop)
+        pkn ^= (pkn ^ in_pkn) & first_mask;
+        r_h = CIN ? (r_h ^ ((r_h ^ in_hf.x) & first_mask)) : (r_h & ~first_mask);
+        r_f = CIN ? (r_f ^ ((r_f ^ in_hf.y) & first_mask)) : (r_f & ~first_mask);
         pk = pkn;
 
         // packed scores of the NEXT column: letter offset code*4096 (the word carries code*4 in byte lane 1).  The
