@@ -18,13 +18,15 @@
 #include "swg_plan.h"
 #include "wavefront.cuh"
 #include "wavefront_q2.cuh"
+#include "wavefront_xw.cuh"
 
 using namespace swg;
 
 namespace {
 
-constexpr uint32_t kDefaultLongCols = 3072;
+constexpr uint32_t kDefaultLongCols = 0;       // 0: the long-tile threshold is estimated per query / launch
 constexpr uint64_t kMaxLongBlocks = 12;
+constexpr uint32_t kXwRingCols = 1024;         // entries of a warp's last-row ring in the long-sequence kernel
 
 struct DeviceBuf {
     void *p = nullptr;
@@ -56,7 +58,7 @@ struct swg_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side_stream = nullptr;      // carries the main search kernel while long tiles run on `stream`
-    cudaEvent_t ev_begin = nullptr, ev_search_end = nullptr, ev_end = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_fork = nullptr, ev_join = nullptr;
     char err[512] = {0};
 
     // resident database shard
@@ -69,6 +71,8 @@ struct swg_ctx {
     uint32_t maxcols = 8;
     double avg_cols = 8;
     std::vector<uint32_t> h_tile_cols;
+    std::vector<uint64_t> h_cols_prefix;      // [ntiles + 1] running sum of h_tile_cols
+    std::vector<uint32_t> h_tile_cols_mono;   // running maximum of h_tile_cols (ascending even when trailing tiles are padding)
     DeviceBuf d_db, d_tile_off, d_tile_cols, d_line_off;
     uint64_t line_units = 0;         // uint2 entries of all per-sequence pass lines (query-pair kernel, multi-pass)
 
@@ -79,12 +83,18 @@ struct swg_ctx {
     std::vector<uint32_t> q_off;     // offsets into d_queries
     int open_gap = 10, extend_gap = 2;
     DeviceBuf d_queries, d_submat;
+    char *h_stage = nullptr;         // pinned staging of the query upload
+    size_t h_stage_cap = 0;
 
     // work buffers
     DeviceBuf d_scores, d_profile, d_profile32, d_boundary, d_counters, d_resc_list, d_topk_scratch, d_top_out;
     DeviceBuf d_profile_q2, d_lines, d_resc_list2, d_q2_counters;
+    DeviceBuf d_profile_xw, d_xw_ring, d_xw_counters, d_xw_list;     // long-sequence kernel (wavefront_xw.cuh)
     std::vector<WorkItem> items;            // schedule of the last run
     std::vector<cudaEvent_t> item_events;   // items.size() + 1 marks
+    std::vector<cudaEvent_t> chunk_events;  // two per chunk of queries, around its top-r selection
+    uint64_t run_chunks = 0, run_window = 0;
+    long score_budget = 4l << 30;           // bytes of score rows a run may keep when the caller wants hit lists only
     std::vector<uint32_t> h_counters;
     std::vector<cudaEvent_t> q_events;      // q_count + 1 marks around every query's kernels
     std::vector<double> q_seconds;
@@ -94,6 +104,8 @@ struct swg_ctx {
 
     // options
     long long_cols = kDefaultLongCols;
+    long xw_warps = 0, xw_rows = 0;         // forced shape of the long-sequence kernel (0: planner)
+    long long_kernel = 1;                   // 1: long tiles run the cross-warp wavefront kernel (K3), 0: the 32-thread shape of K1
     long force_group = 0, force_rows = 0;
     long query_pairing = 1;                 // 0: never pair queries, 1: pair when the planner expects a gain, 2: always
     long q2_group = 0, q2_rows = 0;         // forced shape of the query-pair kernel (0: planner)
@@ -119,7 +131,7 @@ const char *status_text(int st)
     }
 }
 
-char g_last_error[512] = "no error";
+thread_local char g_last_error[512] = "no error";      // per host thread: contexts may be driven concurrently
 
 int fail(swg_ctx *ctx, int st, const char *fmt, ...)
 {
@@ -213,9 +225,15 @@ int finish_load(swg_ctx *ctx, const std::vector<uint16_t> &len, const std::vecto
     ctx->avg_cols = ntiles ? sum_cols / ntiles : 8.0;
     ctx->db_units = tile_off[ntiles];
     ctx->line_units = line_off[ntiles];
-    uint32_t fl = ntiles;
-    while (fl > 0 && ctx->h_tile_cols[fl - 1] > (uint32_t)ctx->long_cols) --fl;   // lengths ascend: long tiles are last
-    ctx->first_long_tile = fl;
+    ctx->h_cols_prefix.assign(ntiles + 1, 0);
+    for (uint32_t t = 0; t < ntiles; ++t) ctx->h_cols_prefix[t + 1] = ctx->h_cols_prefix[t] + ctx->h_tile_cols[t];
+    ctx->h_tile_cols_mono = ctx->h_tile_cols;
+    for (uint32_t t = 1; t < ntiles; ++t)
+        ctx->h_tile_cols_mono[t] = std::max(ctx->h_tile_cols_mono[t], ctx->h_tile_cols_mono[t - 1]);
+    ctx->first_long_tile = ntiles;
+    if (ctx->long_cols > 0)         // lengths ascend: long tiles are last
+        ctx->first_long_tile = (uint32_t)(std::upper_bound(ctx->h_tile_cols_mono.begin(), ctx->h_tile_cols_mono.end(),
+                                                           (uint32_t)ctx->long_cols) - ctx->h_tile_cols_mono.begin());
 
     DeviceBuf d_off, d_len;
     SWG_CUDA(ctx, ctx->d_db.reserve(std::max<uint64_t>(ctx->db_units, 1) * sizeof(uint4)));
@@ -293,7 +311,6 @@ int swg_gpu_create(int device, swg_ctx **out)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_begin);
-    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_search_end);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_end);
     if (e != cudaSuccess) {
         const int st = cuda_fail(nullptr, e, "context creation");
@@ -313,6 +330,7 @@ void swg_gpu_destroy(swg_ctx *ctx)
     free_db(ctx);
     ctx->d_queries.release();
     ctx->d_submat.release();
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     ctx->d_scores.release();
     ctx->d_profile.release();
     ctx->d_profile32.release();
@@ -324,10 +342,14 @@ void swg_gpu_destroy(swg_ctx *ctx)
     ctx->d_profile_q2.release();
     ctx->d_resc_list2.release();
     ctx->d_q2_counters.release();
+    ctx->d_profile_xw.release();
+    ctx->d_xw_ring.release();
+    ctx->d_xw_counters.release();
+    ctx->d_xw_list.release();
     for (cudaEvent_t ev : ctx->q_events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->item_events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
-    if (ctx->ev_search_end) cudaEventDestroy(ctx->ev_search_end);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -344,11 +366,20 @@ int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value)
     if (!strcmp(name, "long_threshold")) {
         if (value != 0 && value < 8) return fail(ctx, SWG_ERR_ARG, "long_threshold must be 0 (automatic) or >= 8");
         ctx->long_cols = value;
-        if (ctx->db_ready) {
-            uint32_t fl = ctx->ntiles;
-            while (fl > 0 && ctx->h_tile_cols[fl - 1] > (uint32_t)value) --fl;
-            ctx->first_long_tile = fl;
-        }
+        if (ctx->db_ready)
+            ctx->first_long_tile = value == 0 ? ctx->ntiles
+                                              : (uint32_t)(std::upper_bound(ctx->h_tile_cols_mono.begin(), ctx->h_tile_cols_mono.end(),
+                                                                            (uint32_t)value) - ctx->h_tile_cols_mono.begin());
+    } else if (!strcmp(name, "long_kernel")) {
+        if (value != 0 && value != 1) return fail(ctx, SWG_ERR_ARG, "long_kernel must be 0 (32-thread shape) or 1 (cross-warp wavefront)");
+        ctx->long_kernel = value;
+    } else if (!strcmp(name, "xw_warps")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+            return fail(ctx, SWG_ERR_ARG, "xw_warps must be 0, 1, 2, 4, 8 or 16");
+        ctx->xw_warps = value;
+    } else if (!strcmp(name, "xw_rows")) {
+        if (value < 0 || value > kMaxRowsPerThread) return fail(ctx, SWG_ERR_ARG, "xw_rows must be 0..32");
+        ctx->xw_rows = value;
     } else if (!strcmp(name, "force_group")) {
         if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32)
             return fail(ctx, SWG_ERR_ARG, "force_group must be 0, 4, 8, 16 or 32");
@@ -369,6 +400,9 @@ int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value)
     } else if (!strcmp(name, "pass_lines")) {
         if (value != 0 && value != 1) return fail(ctx, SWG_ERR_ARG, "pass_lines must be 0 or 1");
         ctx->pass_lines = value;
+    } else if (!strcmp(name, "score_budget_mb")) {
+        if (value < 1) return fail(ctx, SWG_ERR_ARG, "score_budget_mb must be >= 1");
+        ctx->score_budget = value << 20;
     } else if (!strcmp(name, "verbose")) {
         ctx->verbose = value;
     } else if (!strcmp(name, "grid_blocks")) {
@@ -524,16 +558,12 @@ int swg_gpu_load_db_shard(swg_ctx *ctx, const uint16_t *local_lengths, const sig
     return upload_and_build(ctx, len, off, local_residues, nullptr);
 }
 
-int swg_gpu_load_db_interleaved(swg_ctx *ctx, const signed char *vect_db, const uint16_t *vect_lengths, uint64_t vect_count,
-                                const uint64_t *vect_disp, int vector_length, uint64_t n_sequences, int shard, int num_shards)
+// Undo the reference's lane interleave (sequences.c:704-723): lane k of group g holds sequence g*vector_length + k;
+// its residues are vect_db[disp[g] + j*vector_length + k], padded with code 24.
+static void deinterleave(const signed char *vect_db, const uint16_t *vect_lengths, const uint64_t *vect_disp, int vector_length,
+                         uint64_t n_sequences, std::vector<uint16_t> &lengths, std::vector<signed char> &flat)
 {
-    if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
-    if (vector_length != 16 && vector_length != 32) return fail(ctx, SWG_ERR_ARG, "vector_length must be 16 or 32");
-    if (n_sequences > vect_count * (uint64_t)vector_length) return fail(ctx, SWG_ERR_ARG, "more sequences than lanes");
-    if (n_sequences && (!vect_db || !vect_lengths || !vect_disp)) return fail(ctx, SWG_ERR_ARG, "NULL database arrays");
-    // Undo the reference's lane interleave (sequences.c:704-723): lane k of group g holds sequence
-    // g*vector_length + k; its residues are vect_db[disp[g] + j*vector_length + k], padded with code 24.
-    std::vector<uint16_t> lengths(n_sequences);
+    lengths.assign(n_sequences, 0);
     std::vector<uint64_t> start(n_sequences + 1, 0);
     for (uint64_t s = 0; s < n_sequences; ++s) {
         const uint64_t g = s / vector_length, k = s % vector_length;
@@ -543,14 +573,27 @@ int swg_gpu_load_db_interleaved(swg_ctx *ctx, const signed char *vect_db, const 
         lengths[s] = (uint16_t)l;
         start[s + 1] = start[s] + l;
     }
-    std::vector<signed char> flat(std::max<uint64_t>(start[n_sequences], 1));
+    flat.assign(std::max<uint64_t>(start[n_sequences], 1), 0);
     for (uint64_t s = 0; s < n_sequences; ++s) {
         const uint64_t g = s / vector_length, k = s % vector_length;
         const signed char *col = vect_db + vect_disp[g] + k;
         signed char *dst = flat.data() + start[s];
         for (uint32_t j = 0; j < lengths[s]; ++j) dst[j] = col[(uint64_t)j * vector_length];
     }
-    return swg_gpu_load_db(ctx, lengths.data(), flat.data(), n_sequences, start[n_sequences], shard, num_shards);
+    flat.resize(start[n_sequences]);
+}
+
+int swg_gpu_load_db_interleaved(swg_ctx *ctx, const signed char *vect_db, const uint16_t *vect_lengths, uint64_t vect_count,
+                                const uint64_t *vect_disp, int vector_length, uint64_t n_sequences, int shard, int num_shards)
+{
+    if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
+    if (vector_length != 16 && vector_length != 32) return fail(ctx, SWG_ERR_ARG, "vector_length must be 16 or 32");
+    if (n_sequences > vect_count * (uint64_t)vector_length) return fail(ctx, SWG_ERR_ARG, "more sequences than lanes");
+    if (n_sequences && (!vect_db || !vect_lengths || !vect_disp)) return fail(ctx, SWG_ERR_ARG, "NULL database arrays");
+    std::vector<uint16_t> lengths;
+    std::vector<signed char> flat;
+    deinterleave(vect_db, vect_lengths, vect_disp, vector_length, n_sequences, lengths, flat);
+    return swg_gpu_load_db(ctx, lengths.data(), flat.data(), n_sequences, flat.size(), shard, num_shards);
 }
 
 uint64_t swg_gpu_db_local_sequences(const swg_ctx *ctx) { return ctx && ctx->db_ready ? ctx->local_seqs : 0; }
@@ -573,12 +616,25 @@ int swg_gpu_set_queries(swg_ctx *ctx, const signed char *queries, const uint16_t
     const uint64_t total = ctx->q_off[q_count];
     SWG_CUDA(ctx, ctx->d_queries.reserve(std::max<uint64_t>(total, 1)));
     SWG_CUDA(ctx, ctx->d_submat.reserve(768));
-    // queries are packed back to back on the device (the caller's q_disp may leave gaps)
-    for (uint64_t i = 0; i < q_count; ++i)
-        if (q_lengths[i])
-            SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_queries.as<char>() + ctx->q_off[i], queries + q_disp[i], q_lengths[i],
-                                          cudaMemcpyHostToDevice, ctx->stream));
-    SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_submat.p, submat, 768, cudaMemcpyHostToDevice, ctx->stream));
+    // queries are packed back to back (the caller's q_disp may leave gaps) in a pinned staging buffer together with
+    // the matrix, and go to the device in ONE copy: a batch of thousands of queries pays the copy latency once
+    {
+        const size_t need = (size_t)total + 768;
+        if (need > ctx->h_stage_cap) {
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr;
+            ctx->h_stage_cap = 0;
+            SWG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_stage, need + need / 2));
+            ctx->h_stage_cap = need + need / 2;
+        }
+        SWG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // a previous upload may still read the staging buffer
+        for (uint64_t i = 0; i < q_count; ++i)
+            if (q_lengths[i]) memcpy(ctx->h_stage + ctx->q_off[i], queries + q_disp[i], q_lengths[i]);
+        memcpy(ctx->h_stage + total, submat, 768);
+        SWG_CUDA(ctx, ctx->d_queries.reserve(need));
+        SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_queries.p, ctx->h_stage, need, cudaMemcpyHostToDevice, ctx->stream));
+        SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_submat.p, ctx->d_queries.as<char>() + total, 768, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     ctx->open_gap = open_gap;
     ctx->extend_gap = extend_gap;
     ctx->queries_ready = true;
@@ -589,7 +645,6 @@ int swg_gpu_set_queries(swg_ctx *ctx, const signed char *queries, const uint16_t
 
 int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
 {
-    (void)keep_scores;
     if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
     if (!ctx->db_ready) return fail(ctx, SWG_ERR_STATE, "no database loaded");
     if (!ctx->queries_ready) return fail(ctx, SWG_ERR_STATE, "no queries set");
@@ -616,6 +671,18 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
         lines_fit = (double)ctx->line_units * sizeof(uint2) < 0.6 * (double)free_b;
     }
+    // ---- score rows: a window of queries ----
+    // All nq rows when the caller wants the full score vectors.  Otherwise at most `score_budget` bytes of rows: the
+    // batch is searched in chunks of that many queries, each chunk followed by its own top-r selection, so that a
+    // batch of a thousand queries on a multi-million-sequence shard does not need nq x n x 4 bytes.
+    uint64_t window = nq;
+    if (!keep_scores && nq > 2 && n_pad)
+        window = std::min<uint64_t>(nq, std::max<uint64_t>(2, (uint64_t)ctx->score_budget / (n_pad * sizeof(int32_t))));
+    const uint64_t nchunks = nq ? (nq + window - 1) / window : 1;
+    window = nq ? (nq + nchunks - 1) / nchunks : 0;           // chunks of equal size
+    ctx->run_kept_scores = nchunks == 1;
+    ctx->run_window = window;
+
     ShardShape shape;
     shape.residues = ctx->local_residues;
     shape.maxcols = ctx->maxcols;
@@ -627,13 +694,33 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     opts.q2_rows = ctx->q2_rows;
     opts.force_group = ctx->force_group;
     opts.force_rows = ctx->force_rows;
-    std::vector<Config> main_cfgs, wide_cfgs;
+    std::vector<Config> main_cfgs(nq), wide_cfgs(nq);
     std::vector<WorkItem> &items = ctx->items;
+    std::vector<size_t> chunk_end;                      // items [chunk_end[c-1], chunk_end[c]) belong to chunk c
     uint32_t max_passes = 1, q2_launches = 0;
     bool q2_lines = false;
     const uint64_t dummy_lines = warps * 4 * (uint64_t)(kQ2MinSegCols + kQ2LineSlack);     // one per thread group (G >= 8)
     for (int attempt = 0; attempt < 2; ++attempt) {
-        plan_batch(ctx->q_len, shape, opts, main_cfgs, wide_cfgs, items);
+        items.clear();
+        chunk_end.clear();
+        for (uint64_t c = 0; c < nchunks; ++c) {
+            // every chunk is planned on its own (queries are paired inside a chunk); ids become batch-wide afterwards
+            const uint64_t q0 = c * window, q1 = std::min(nq, q0 + window);
+            const std::vector<uint16_t> sub_len(ctx->q_len.begin() + q0, ctx->q_len.begin() + q1);
+            std::vector<Config> sub_main, sub_wide;
+            std::vector<WorkItem> sub_items;
+            plan_batch(sub_len, shape, opts, sub_main, sub_wide, sub_items);
+            for (uint64_t i = 0; i < q1 - q0; ++i) { main_cfgs[q0 + i] = sub_main[i]; wide_cfgs[q0 + i] = sub_wide[i]; }
+            for (WorkItem &it : sub_items) {
+                it.qa += (uint32_t)q0;
+                for (uint32_t &m : it.members) m += (uint32_t)q0;
+                for (Q2Launch &L : it.launches)
+                    for (int l = 0; l < 2; ++l)
+                        if (L.lane[l].q >= 0) L.lane[l].q += (int32_t)q0;
+                items.push_back(std::move(it));
+            }
+            chunk_end.push_back(items.size());
+        }
         max_passes = 1;
         q2_launches = 0;
         q2_lines = false;
@@ -652,18 +739,76 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     }
     if (ctx->verbose) fputs(describe_plan(ctx->q_len, main_cfgs, items).c_str(), stderr);
 
-    SWG_CUDA(ctx, ctx->d_scores.reserve(std::max<uint64_t>(nq * n_pad, 1) * sizeof(int32_t)));
+    // ---- long tiles (K3) ----
+    // A sequence is a serial chain of (columns x passes) steps of its thread group, so a very long one can outlast the
+    // whole rest of a launch.  Per work item: the first tile whose chain would come close to the estimated time of the
+    // item's launches (option long_threshold > 0: a fixed column count instead).  Those tiles leave the item's main
+    // launches and are searched, query by query, by the long-sequence kernel (wavefront_xw.cuh) on the high-priority
+    // stream, while the main launches fill the other SMs from the side stream.
+    std::vector<uint32_t> item_first_long(items.size(), ctx->ntiles);
+    std::vector<XwConfig> xw_cfgs(nq);
+    bool any_xw = false;
+    if (ctx->ntiles) {
+        const double res9 = (double)ctx->local_residues * 1e-9;
+        for (size_t ii = 0; ii < items.size(); ++ii) {
+            const WorkItem &it = items[ii];
+            double limit = 1e300;
+            bool xw_ok = ctx->long_kernel != 0;
+            if (it.pair) {
+                for (const Q2Launch &L : it.launches)
+                    limit = std::min(limit, long_tile_limit(2.0 * L.G * L.K / q2_rate(L.G, L.K, it.launches.size() > 1) * res9, L.K, 1));
+                for (uint32_t q : it.members) xw_ok = xw_ok && ctx->q_len[q] <= (uint32_t)kXwMaxRows;
+                if (!xw_ok) continue;          // the pair kernel keeps every tile
+            } else {
+                const Config &c = main_cfgs[it.qa];
+                limit = long_tile_limit((double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes) * res9, c.K, c.passes);
+                xw_ok = xw_ok && ctx->q_len[it.qa] <= (uint32_t)kXwMaxRows;
+            }
+            uint32_t fl = ctx->ntiles;
+            if (ctx->long_cols > 0) fl = ctx->first_long_tile;
+            else if ((double)ctx->maxcols > 1.125 * limit)
+                fl = (uint32_t)(std::upper_bound(ctx->h_tile_cols_mono.begin(), ctx->h_tile_cols_mono.end(),
+                                                 (uint32_t)std::min(limit, 4.0e9)) - ctx->h_tile_cols_mono.begin());
+            item_first_long[ii] = fl;
+            if (fl >= ctx->ntiles || !xw_ok) continue;
+            const double long_res = (double)(ctx->h_cols_prefix[ctx->ntiles] - ctx->h_cols_prefix[fl]) * kTileSeqs;
+            const std::vector<uint32_t> qs = it.pair ? it.members : std::vector<uint32_t>(1, it.qa);
+            bool all_ok = true;
+            for (uint32_t q : qs) {
+                xw_cfgs[q] = choose_xw_config(ctx->q_len[q], long_res, (double)ctx->maxcols, ctx->xw_warps, ctx->xw_rows);
+                all_ok = all_ok && xw_cfgs[q].ok();
+            }
+            if (!all_ok) {                     // (a forced shape too small for the query)
+                for (uint32_t q : qs) xw_cfgs[q] = XwConfig();
+                if (it.pair) item_first_long[ii] = ctx->ntiles;
+                continue;
+            }
+            any_xw = true;
+            if (ctx->verbose)
+                for (uint32_t q : qs)
+                    fprintf(stderr, "[swg] query %u (%u rows): tiles %u..%u (%.0f columns x 16) on the long-sequence kernel, %d warps x %d rows\n",
+                            q, (unsigned)ctx->q_len[q], fl, ctx->ntiles - 1, long_res / kTileSeqs, xw_cfgs[q].W, xw_cfgs[q].K);
+        }
+    }
+
+    SWG_CUDA(ctx, ctx->d_scores.reserve(std::max<uint64_t>(window * n_pad, 1) * sizeof(int32_t)));
     SWG_CUDA(ctx, ctx->d_profile.reserve((size_t)max_passes * kPassBytes));
     SWG_CUDA(ctx, ctx->d_profile32.reserve((size_t)max_passes * kPassBytes));
     SWG_CUDA(ctx, ctx->d_boundary.reserve(2 * warps * (size_t)(ctx->maxcols + kBoundarySlack) * sizeof(uint2)));
     SWG_CUDA(ctx, ctx->d_counters.reserve(std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t)));
+    SWG_CUDA(ctx, ctx->d_xw_counters.reserve(std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t)));
     SWG_CUDA(ctx, ctx->d_resc_list.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
     if (q2_launches) {
         SWG_CUDA(ctx, ctx->d_profile_q2.reserve((size_t)kQ2ProfileBytes));
         SWG_CUDA(ctx, ctx->d_resc_list2.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
         SWG_CUDA(ctx, ctx->d_q2_counters.reserve((size_t)q2_launches * sizeof(uint32_t)));
     }
-    const TopkPlan tp = topk_plan(n_pad, top, nq);
+    if (any_xw) {
+        SWG_CUDA(ctx, ctx->d_profile_xw.reserve((size_t)16 * kPassBytes));
+        SWG_CUDA(ctx, ctx->d_xw_ring.reserve((size_t)ctx->sm_count * 16 * kXwRingCols * sizeof(uint2)));
+        SWG_CUDA(ctx, ctx->d_xw_list.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
+    }
+    const TopkPlan tp = topk_plan(n_pad, top, window);
     SWG_CUDA(ctx, ctx->d_topk_scratch.reserve(tp.scratch_keys * sizeof(uint64_t)));
     SWG_CUDA(ctx, ctx->d_top_out.reserve(std::max<uint64_t>(nq * top, 1) * sizeof(uint64_t)));
 
@@ -694,15 +839,25 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                                   (c.global_profile ? 2u : 0u));
             if (we == cudaSuccess && fresh(key)) we = launch_wavefront(lane32, c, 1, ctx->stream, w);
         };
+        auto warm_xw = [&](const XwConfig &xc) {
+            if (!xc.ok()) return;
+            w.profile = ctx->d_profile_xw.as<uint8_t>();
+            w.xw_warps = (uint32_t)xc.W;
+            w.xw_ring_cols = kXwRingCols;
+            w.xw_ring = ctx->d_xw_ring.as<uint2>();
+            if (we == cudaSuccess && fresh((2u << 20) + (uint32_t)xc.K)) we = launch_xw_l16(xc.K, 1, ctx->stream, w);
+            if (we == cudaSuccess && fresh((3u << 20) + (uint32_t)xc.K)) we = launch_xw_l32(xc.K, 1, ctx->stream, w);
+        };
         for (const WorkItem &it : items) {
             if (!ctx->ntiles) break;
             if (!it.pair) {
                 warm_seqpair(false, main_cfgs[it.qa]);
                 warm_seqpair(false, wide_cfgs[it.qa]);
                 warm_seqpair(true, wide_cfgs[it.qa]);
+                warm_xw(xw_cfgs[it.qa]);
                 continue;
             }
-            for (uint32_t q : it.members) warm_seqpair(true, wide_cfgs[q]);
+            for (uint32_t q : it.members) { warm_seqpair(true, wide_cfgs[q]); warm_xw(xw_cfgs[q]); }
             w.profile = ctx->d_profile_q2.as<uint8_t>();
             for (const Q2Launch &L : it.launches) {
                 bool cin = false, cout = false;
@@ -717,6 +872,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
 
     SWG_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t), ctx->stream));
+    SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_xw_counters.p, 0, std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t), ctx->stream));
     if (q2_launches) SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_q2_counters.p, 0, (size_t)q2_launches * sizeof(uint32_t), ctx->stream));
 
     WfParams p;
@@ -742,20 +898,28 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     SWG_CUDA(ctx, cudaEventRecord(ctx->item_events[0], ctx->stream));
     uint64_t padded = 0;
     uint32_t q2_next_counter = 0;
+    uint64_t chunk_q0 = 0;                               // first query of the chunk being enqueued
+    auto score_row = [&](uint64_t q) { return ctx->d_scores.as<int32_t>() + (q - chunk_q0) * n_pad; };
+    while (ctx->chunk_events.size() < 2 * nchunks) {
+        cudaEvent_t ev;
+        SWG_CUDA(ctx, cudaEventCreate(&ev));
+        ctx->chunk_events.push_back(ev);
+    }
+    ctx->run_chunks = 0;
 
     // 32-bit recomputation (K2) of the sequences query q left in `list`
-    auto recompute32 = [&](uint64_t q, uint32_t *list, bool build) -> cudaError_t {
+    auto recompute32 = [&](uint64_t q, uint32_t *list, bool build, cudaStream_t st) -> cudaError_t {
         const Config wide_cfg = wide_cfgs[q];
         uint32_t *cnt = ctx->d_counters.as<uint32_t>() + q * 4;
         cudaError_t e = cudaSuccess;
         if (build) {
             e = launch_build_profile(ctx->d_queries.as<int8_t>() + ctx->q_off[q], ctx->q_len[q], ctx->d_submat.as<int8_t>(),
-                                     wide_cfg.G, wide_cfg.K, wide_cfg.passes, ctx->d_profile32.as<uint8_t>(), ctx->stream);
+                                     wide_cfg.G, wide_cfg.K, wide_cfg.passes, ctx->d_profile32.as<uint8_t>(), st);
             ctx->stats.launches += 1;
         }
         if (e != cudaSuccess) return e;
         WfParams r = p;
-        r.scores = ctx->d_scores.as<int32_t>() + q * n_pad;
+        r.scores = score_row(q);
         r.profile = ctx->d_profile32.as<uint8_t>();
         r.passes = wide_cfg.passes;
         r.tile_first = 0;
@@ -764,14 +928,93 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         r.resc_count = cnt + 3;
         r.resc_list = list;
         ctx->stats.launches += 1;
-        return launch_wavefront(true, wide_cfg, grid, ctx->stream, r);
+        return launch_wavefront(true, wide_cfg, grid, st, r);
     };
 
+    // Long tiles [fl, ntiles) of query q on the long-sequence kernel (K3): profile of all W passes, the 16-bit launch
+    // (scores merged with atomicMax, hence zeroed first), and the 32-bit recomputation of what it listed, same shape.
+    auto enqueue_xw = [&](uint64_t q, uint32_t fl, int xgrid, cudaStream_t st) -> cudaError_t {
+        const XwConfig xc = xw_cfgs[q];
+        uint32_t *xcnt = ctx->d_xw_counters.as<uint32_t>() + q * 4;
+        int32_t *sc = score_row(q);
+        cudaError_t e = launch_build_profile(ctx->d_queries.as<int8_t>() + ctx->q_off[q], ctx->q_len[q], ctx->d_submat.as<int8_t>(),
+                                             32, xc.K, (uint32_t)xc.W, ctx->d_profile_xw.as<uint8_t>(), st);
+        if (e == cudaSuccess)
+            e = cudaMemsetAsync(sc + (size_t)fl * kTileSeqs, 0, (size_t)(ctx->ntiles - fl) * kTileSeqs * sizeof(int32_t), st);
+        if (e != cudaSuccess) return e;
+        WfParams x = p;
+        x.scores = sc;
+        x.profile = ctx->d_profile_xw.as<uint8_t>();
+        x.passes = (uint32_t)xc.W;
+        x.tile_first = fl;
+        x.tile_count = ctx->ntiles - fl;
+        x.task_counter = xcnt + 0;
+        x.resc_count = xcnt + 1;
+        x.resc_list = ctx->d_xw_list.as<uint32_t>();
+        x.xw_warps = (uint32_t)xc.W;
+        x.xw_ring_cols = kXwRingCols;
+        x.xw_ring = ctx->d_xw_ring.as<uint2>();
+        e = launch_xw_l16(xc.K, xgrid, st, x);
+        x.task_counter = xcnt + 2;
+        if (e == cudaSuccess) e = launch_xw_l32(xc.K, xgrid, st, x);
+        ctx->stats.launches += 3;
+        ctx->stats.cells += 0;
+        for (uint32_t t = fl; t < ctx->ntiles; ++t)
+            padded += (uint64_t)xc.W * 32 * xc.K * (ctx->h_tile_cols[t] + 40) * kTileSeqs;
+        return e;
+    };
+    // CTAs for the long tiles of one query: in proportion to their share of the columns (the long and the main launches
+    // run side by side, one CTA per SM), at least kMaxLongBlocks when there is that much work
+    auto long_grid_for = [&](uint32_t fl, uint64_t groups_needed, bool main_runs) -> int {
+        const double long_cols_sum = (double)(ctx->h_cols_prefix[ctx->ntiles] - ctx->h_cols_prefix[fl]);
+        const double share = long_cols_sum / std::max(1.0, (double)ctx->h_cols_prefix[ctx->ntiles]);
+        const uint64_t by_share = (uint64_t)(share * grid + 0.999);
+        int lg = (int)std::min<uint64_t>(std::max<uint64_t>(groups_needed, 1), std::max<uint64_t>(kMaxLongBlocks, by_share));
+        if (lg > grid - 1 && main_runs) lg = std::max(1, grid - 1);
+        if (!main_runs) lg = (int)std::min<uint64_t>(std::max<uint64_t>(groups_needed, 1), (uint64_t)grid);
+        return lg;
+    };
+
+    size_t chunk_of_item = 0;
     for (size_t ii = 0; ii < items.size() && ctx->ntiles; ++ii) {
+        while (ii >= chunk_end[chunk_of_item]) ++chunk_of_item;
+        chunk_q0 = chunk_of_item * window;
+        const bool chunk_ends_here = ii + 1 == chunk_end[chunk_of_item];
+        // the top-r selection of a finished chunk (its score rows are reused by the next chunk)
+        auto finish_chunk = [&]() -> int {
+            const uint64_t q1 = std::min(nq, chunk_q0 + window);
+            SWG_CUDA(ctx, cudaEventRecord(ctx->chunk_events[2 * chunk_of_item], ctx->stream));
+            if (top) {
+                cudaError_t te = launch_topk(tp, ctx->d_scores.as<int32_t>(), q1 - chunk_q0, ctx->n_total, ctx->shard,
+                                             ctx->num_shards, ctx->d_topk_scratch.as<uint64_t>(),
+                                             ctx->d_top_out.as<uint64_t>() + chunk_q0 * top, ctx->stream, &ctx->stats.launches);
+                if (te != cudaSuccess) return cuda_fail(ctx, te, "top-r launch");
+            }
+            SWG_CUDA(ctx, cudaEventRecord(ctx->chunk_events[2 * chunk_of_item + 1], ctx->stream));
+            ctx->run_chunks = chunk_of_item + 1;
+            return SWG_OK;
+        };
         const WorkItem &it = items[ii];
         if (it.pair) {
-            // ---- two queries per register: one launch per pass over the whole shard ----
+            // ---- two queries per register: one launch per pass over the shard's tiles below the long-tile threshold ----
             cudaError_t e = cudaSuccess;
+            const uint32_t main_tiles = item_first_long[ii];
+            cudaStream_t ks = ctx->stream;               // stream of the pair kernel's launches
+            bool forked = false;
+            if (main_tiles < ctx->ntiles) {
+                if (main_tiles) {
+                    e = cudaEventRecord(ctx->ev_fork, ctx->stream);
+                    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
+                    forked = e == cudaSuccess;
+                    if (forked) ks = ctx->side_stream;
+                }
+                for (size_t k = 0; k < it.members.size() && e == cudaSuccess; ++k) {
+                    const uint32_t q = it.members[k];
+                    const uint64_t groups = ((uint64_t)(ctx->ntiles - main_tiles) * kTilePairs * xw_cfgs[q].W + 15) / 16;
+                    e = enqueue_xw(q, main_tiles, long_grid_for(main_tiles, groups, main_tiles > 0), ctx->stream);
+                }
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "long-sequence kernel launch");
+            }
             auto lane_q = [&](const LaneSlice &sl) { return sl.q >= 0 ? ctx->d_queries.as<int8_t>() + ctx->q_off[sl.q] : nullptr; };
             auto lane_m = [&](const LaneSlice &sl) { return sl.q >= 0 ? (uint32_t)ctx->q_len[sl.q] : 0u; };
             WfParams pq = p;
@@ -781,9 +1024,9 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             pq.line_off = ctx->d_line_off.as<uint64_t>();
             pq.line_dummy = ctx->line_units;
             pq.tile_first = 0;
-            pq.tile_count = ctx->ntiles;
+            pq.tile_count = main_tiles;
             pq.passes = 1;
-            for (size_t li = 0; li < it.launches.size() && e == cudaSuccess; ++li) {
+            for (size_t li = 0; li < it.launches.size() && e == cudaSuccess && main_tiles; ++li) {
                 const Q2Launch &L = it.launches[li];
                 bool cin = false, cout = false;
                 uint32_t cin_mask = 0;
@@ -793,7 +1036,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                     int32_t *sc = nullptr;
                     uint32_t *rc = nullptr;
                     if (sl.q >= 0) {
-                        sc = ctx->d_scores.as<int32_t>() + (uint64_t)sl.q * n_pad;
+                        sc = score_row((uint64_t)sl.q);
                         rc = ctx->d_counters.as<uint32_t>() + (uint64_t)sl.q * 4 + 3;
                         pq.lane_flags |= (kLaneActive | (sl.first ? kLaneFirst : 0u)) << (2 * l);
                         if (!sl.first) { cin = true; cin_mask |= 0xffffu << (16 * l); }
@@ -804,7 +1047,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 }
                 if (cin && cin_mask != 0xffffffffu) {
                     // one lane continues, the other starts a query (or idles): its half of the lines must read as zero
-                    e = launch_clear_lane(ctx->d_lines.as<uint2>(), ctx->line_units, cin_mask, ctx->stream);
+                    e = launch_clear_lane(ctx->d_lines.as<uint2>(), ctx->line_units, cin_mask, ks);
                     ctx->stats.launches += 1;
                     ctx->stats.stream_bytes += 2 * ctx->line_units * sizeof(uint2);
                     if (e != cudaSuccess) break;
@@ -812,25 +1055,30 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 // the launch's profile (one slot: the stream orders the build behind the previous launch, 100 KB, ~5 us)
                 e = launch_build_profile_q2(lane_q(L.lane[0]), lane_m(L.lane[0]), lane_q(L.lane[1]), lane_m(L.lane[1]),
                                             ctx->d_submat.as<int8_t>(), L.G, L.K, L.lane[0].row0, L.lane[1].row0,
-                                            ctx->d_profile_q2.as<uint8_t>(), ctx->stream);
+                                            ctx->d_profile_q2.as<uint8_t>(), ks);
                 ctx->stats.launches += 1;
                 if (e != cudaSuccess) break;
                 pq.profile = ctx->d_profile_q2.as<uint8_t>();
                 pq.task_counter = ctx->d_q2_counters.as<uint32_t>() + q2_next_counter++;
-                e = launch_q2(L.G, L.K, cin, cout, grid, ctx->stream, pq);
+                e = launch_q2(L.G, L.K, cin, cout, grid, ks, pq);
                 ctx->stats.launches += 1;
                 ctx->stats.pair_launches += 1;
                 ctx->stats.stream_bytes += ctx->db_units * sizeof(uint4) + ((int)cin + (int)cout) * ctx->line_units * sizeof(uint2);
-                padded += 2ull * L.G * L.K * (uint64_t)((ctx->avg_cols + L.G - 1) * ctx->ntiles) * kTileSeqs;
+                padded += 2ull * L.G * L.K * (uint64_t)((ctx->avg_cols + L.G - 1) * main_tiles) * kTileSeqs;
                 // a query that ends here: its overflowed sequences are recomputed before the lane's list is reused
                 for (int l = 0; l < 2 && e == cudaSuccess; ++l)
                     if (L.lane[l].q >= 0 && L.lane[l].last)
                         e = recompute32((uint64_t)L.lane[l].q, l == 0 ? ctx->d_resc_list.as<uint32_t>()
-                                                                       : ctx->d_resc_list2.as<uint32_t>(), true);
+                                                                       : ctx->d_resc_list2.as<uint32_t>(), true, ks);
+            }
+            if (e == cudaSuccess && forked) {
+                e = cudaEventRecord(ctx->ev_join, ctx->side_stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
             }
             if (e != cudaSuccess) return cuda_fail(ctx, e, "query-pair kernel launch");
             SWG_CUDA(ctx, cudaEventRecord(ctx->item_events[ii + 1], ctx->stream));
             ctx->stats.cells += it.member_rows * ctx->local_residues;
+            if (chunk_ends_here) { const int fs = finish_chunk(); if (fs != SWG_OK) return fs; }
             continue;
         }
         const uint64_t q = it.qa;
@@ -839,7 +1087,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         const Config wide_cfg = wide_cfgs[q];
         uint32_t *cnt = ctx->d_counters.as<uint32_t>() + q * 4;
         const int8_t *d_q = ctx->d_queries.as<int8_t>() + ctx->q_off[q];
-        p.scores = ctx->d_scores.as<int32_t>() + q * n_pad;
+        p.scores = score_row(q);
         p.resc_count = cnt + 3;
 
         cudaError_t e = launch_build_profile(d_q, m, ctx->d_submat.as<int8_t>(), wide_cfg.G, wide_cfg.K, wide_cfg.passes,
@@ -852,60 +1100,40 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                                      ctx->d_profile.as<uint8_t>(), ctx->stream);
             ctx->stats.launches += 1;
         }
-        // Long tiles: a sequence is a serial chain of (columns x passes) steps, so a very long one can outlast the
-        // whole rest of the search.  Such tiles go to the 32-thread shape (the shortest step) and start first, on a
-        // few SMs of their own, while the main kernel (launched on the low-priority side stream right behind) fills
-        // the others.  Whether a tile is "long" is decided per query from the estimated run times.
-        uint32_t first_long = ctx->ntiles;
-        if (!same) {
-            if (ctx->long_cols > 0) first_long = ctx->first_long_tile;
-            else {
-                const double total_cycles = (double)m * (double)ctx->local_residues /
-                                            (shape_rate(main_cfg.G, main_cfg.K, main_cfg.passes) * 1e9) * kSmHz;
-                // cycles per column of one thread group on a busy SM (about 24 per row, measured on the long-sequence
-                // workload; the same model the batch planner uses)
-                const double step = (24.0 * main_cfg.K + 100.0) * main_cfg.passes;
-                // the 32-thread shape is the less efficient one (few rows per thread): it gets only the tiles whose
-                // chain on the main shape would come close to the whole run
-                const double limit_cols = 0.8 * total_cycles / step;
-                if ((double)ctx->maxcols > 0.9 * total_cycles / step) {
-                    first_long = (uint32_t)(std::upper_bound(ctx->h_tile_cols.begin(), ctx->h_tile_cols.end(),
-                                                             (uint32_t)std::min(limit_cols, 4.0e9)) - ctx->h_tile_cols.begin());
-                }
-            }
-        }
+        // Long tiles start first, on a few SMs of their own (high-priority stream), while the main kernel (launched on
+        // the low-priority side stream right behind) fills the others.  They run the long-sequence kernel; queries it
+        // does not cover (more than 8192 rows) and option long_kernel = 0 fall back to the 32-thread shape of this kernel.
+        uint32_t first_long = item_first_long[ii];
+        const bool use_xw = first_long < ctx->ntiles && xw_cfgs[q].ok();
+        if (!use_xw && same) first_long = ctx->ntiles;          // the main shape IS the 32-thread shape
         uint32_t main_tiles = ctx->ntiles;
         bool forked = false;
         if (e == cudaSuccess && first_long < ctx->ntiles) {
             main_tiles = first_long;
             const uint32_t long_tiles = ctx->ntiles - first_long;
-            const uint64_t long_warps = (uint64_t)long_tiles * kTilePairs;          // one pair per warp at G = 32
-            // SMs for the long tiles: in proportion to their share of the columns (the two launches run side by
-            // side, one CTA per SM), at least kMaxLongBlocks when there are that many warps of work
-            double long_cols_sum = 0.0;
-            for (uint32_t t = first_long; t < ctx->ntiles; ++t) long_cols_sum += ctx->h_tile_cols[t];
-            const double share = long_cols_sum / std::max(1.0, ctx->avg_cols * ctx->ntiles);
-            const uint64_t by_share = (uint64_t)(share * grid + 0.999);
-            int long_grid = (int)std::min<uint64_t>((long_warps + warps_per_block - 1) / warps_per_block,
-                                                    std::max<uint64_t>(kMaxLongBlocks, by_share));
-            if (long_grid > grid - 1 && main_tiles) long_grid = grid - 1;
-            if (main_tiles == 0) long_grid = grid;                                    // nothing else to run
-            p.profile = ctx->d_profile32.as<uint8_t>();
-            p.passes = wide_cfg.passes;
-            p.tile_first = first_long;
-            p.tile_count = long_tiles;
-            p.task_counter = cnt + 0;
-            p.boundary = ctx->d_boundary.as<uint2>() + warps * (size_t)p.maxcols;      // its own scratch lines
             if (main_tiles) {
                 e = cudaEventRecord(ctx->ev_fork, ctx->stream);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
                 forked = e == cudaSuccess;
             }
-            if (e == cudaSuccess) e = launch_wavefront(false, wide_cfg, long_grid, ctx->stream, p);
-            p.boundary = ctx->d_boundary.as<uint2>();
-            ctx->stats.launches += 1;
-            for (uint32_t t = p.tile_first; t < ctx->ntiles; ++t)
-                padded += (uint64_t)wide_cfg.passes * wide_cfg.G * wide_cfg.K * (ctx->h_tile_cols[t] + wide_cfg.G - 1) * kTileSeqs;
+            if (use_xw) {
+                const uint64_t groups = ((uint64_t)long_tiles * kTilePairs * xw_cfgs[q].W + 15) / 16;
+                if (e == cudaSuccess) e = enqueue_xw(q, first_long, long_grid_for(first_long, groups, main_tiles > 0), ctx->stream);
+            } else {
+                const uint64_t long_warps = (uint64_t)long_tiles * kTilePairs;          // one pair per warp at G = 32
+                const int long_grid = long_grid_for(first_long, (long_warps + warps_per_block - 1) / warps_per_block, main_tiles > 0);
+                p.profile = ctx->d_profile32.as<uint8_t>();
+                p.passes = wide_cfg.passes;
+                p.tile_first = first_long;
+                p.tile_count = long_tiles;
+                p.task_counter = cnt + 0;
+                p.boundary = ctx->d_boundary.as<uint2>() + warps * (size_t)p.maxcols;      // its own scratch lines
+                if (e == cudaSuccess) e = launch_wavefront(false, wide_cfg, long_grid, ctx->stream, p);
+                p.boundary = ctx->d_boundary.as<uint2>();
+                ctx->stats.launches += 1;
+                for (uint32_t t = p.tile_first; t < ctx->ntiles; ++t)
+                    padded += (uint64_t)wide_cfg.passes * wide_cfg.G * wide_cfg.K * (ctx->h_tile_cols[t] + wide_cfg.G - 1) * kTileSeqs;
+            }
         }
         if (e == cudaSuccess && main_tiles) {
             p.profile = same ? ctx->d_profile32.as<uint8_t>() : ctx->d_profile.as<uint8_t>();
@@ -918,24 +1146,17 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             ctx->stats.launches += 1;
         }
         if (e == cudaSuccess && forked) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
-        if (e == cudaSuccess) e = recompute32(q, ctx->d_resc_list.as<uint32_t>(), false);
+        if (e == cudaSuccess) e = recompute32(q, ctx->d_resc_list.as<uint32_t>(), false, ctx->stream);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "search kernel launch");
         SWG_CUDA(ctx, cudaEventRecord(ctx->item_events[ii + 1], ctx->stream));
         ctx->stats.cells += (uint64_t)m * ctx->local_residues;
         ctx->stats.stream_bytes += ctx->db_units * sizeof(uint4);
         padded += (uint64_t)main_cfg.passes * main_cfg.G * main_cfg.K *
                   (uint64_t)((ctx->avg_cols + main_cfg.G - 1) * main_tiles) * kTileSeqs;
+        if (chunk_ends_here) { const int fs = finish_chunk(); if (fs != SWG_OK) return fs; }
     }
     ctx->stats.padded_cells = padded;
-    SWG_CUDA(ctx, cudaEventRecord(ctx->ev_search_end, ctx->stream));
-    if (ctx->ntiles && top) {
-        cudaError_t e = launch_topk(tp, ctx->d_scores.as<int32_t>(), nq, ctx->n_total, ctx->shard, ctx->num_shards,
-                                    ctx->d_topk_scratch.as<uint64_t>(), ctx->d_top_out.as<uint64_t>(), ctx->stream,
-                                    &ctx->stats.launches);
-        if (e != cudaSuccess) return cuda_fail(ctx, e, "top-r launch");
-    } else if (nq * top) {
-        SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_top_out.p, 0, nq * top * sizeof(uint64_t), ctx->stream));
-    }
+    if (!ctx->ntiles && nq * top) SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_top_out.p, 0, nq * top * sizeof(uint64_t), ctx->stream));
     SWG_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
     ctx->run_done = true;
     return SWG_OK;
@@ -947,12 +1168,16 @@ int swg_gpu_sync(swg_ctx *ctx)
     SWG_CUDA(ctx, cudaSetDevice(ctx->device));
     SWG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->run_done) {
-        float ms_all = 0.f, ms_search = 0.f;
+        float ms_all = 0.f, ms_topr = 0.f;
         SWG_CUDA(ctx, cudaEventElapsedTime(&ms_all, ctx->ev_begin, ctx->ev_end));
-        SWG_CUDA(ctx, cudaEventElapsedTime(&ms_search, ctx->ev_begin, ctx->ev_search_end));
+        for (uint64_t c = 0; c < ctx->run_chunks; ++c) {
+            float ms = 0.f;
+            SWG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->chunk_events[2 * c], ctx->chunk_events[2 * c + 1]));
+            ms_topr += ms;
+        }
         ctx->stats.device_seconds = ms_all * 1e-3;
-        ctx->stats.search_seconds = ms_search * 1e-3;
-        ctx->stats.topr_seconds = (ms_all - ms_search) * 1e-3;
+        ctx->stats.search_seconds = (ms_all - ms_topr) * 1e-3;
+        ctx->stats.topr_seconds = ms_topr * 1e-3;
         ctx->q_seconds.assign(ctx->q_count, 0.0);
         for (size_t ii = 0; ii < ctx->items.size() && ctx->ntiles; ++ii) {
             float ms = 0.f;
@@ -971,6 +1196,8 @@ int swg_gpu_fetch(swg_ctx *ctx, int32_t *scores, uint64_t *top_keys)
 {
     if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
     if (!ctx->run_done) return fail(ctx, SWG_ERR_STATE, "fetch without a run");
+    if (scores && !ctx->run_kept_scores)
+        return fail(ctx, SWG_ERR_STATE, "the run did not keep every query's score row (swg_gpu_run with keep_scores = 0)");
     SWG_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t nq = ctx->q_count, n_pad = (uint64_t)ctx->ntiles * kTileSeqs;
     uint64_t d2h = 0;
@@ -985,28 +1212,43 @@ int swg_gpu_fetch(swg_ctx *ctx, int32_t *scores, uint64_t *top_keys)
     }
     std::vector<int32_t> local;
     if (scores && nq * n_pad) {
-        local.resize(nq * n_pad);
-        SWG_CUDA(ctx, cudaMemcpyAsync(local.data(), ctx->d_scores.p, nq * n_pad * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                      ctx->stream));
-        d2h += nq * n_pad * sizeof(int32_t);
+        // local (tile-sharded) order -> positions in the whole length-sorted database.  One shard: a query's local
+        // row IS the global row (2-D copy, the pad lanes of the last tile are dropped); several shards: local tile lt is
+        // global tile lt * num_shards + shard, so the rows are scattered tile by tile (64 bytes) from a staging copy.
+        if (ctx->num_shards == 1) {
+            SWG_CUDA(ctx, cudaMemcpy2DAsync(scores, ctx->n_total * sizeof(int32_t), ctx->d_scores.p, n_pad * sizeof(int32_t),
+                                            ctx->n_total * sizeof(int32_t), nq, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            local.resize(nq * n_pad);
+            SWG_CUDA(ctx, cudaMemcpyAsync(local.data(), ctx->d_scores.p, nq * n_pad * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                          ctx->stream));
+        }
+        d2h += nq * ctx->local_seqs * sizeof(int32_t);
     }
     uint32_t resc = 0;
-    std::vector<uint32_t> cnt(std::max<uint64_t>(nq, 1) * 4, 0);
-    if (nq)
+    std::vector<uint32_t> cnt(std::max<uint64_t>(nq, 1) * 4, 0), xcnt(std::max<uint64_t>(nq, 1) * 4, 0);
+    if (nq) {
         SWG_CUDA(ctx, cudaMemcpyAsync(cnt.data(), ctx->d_counters.p, nq * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                       ctx->stream));
+        SWG_CUDA(ctx, cudaMemcpyAsync(xcnt.data(), ctx->d_xw_counters.p, nq * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    }
     const int st = swg_gpu_sync(ctx);
     if (st != SWG_OK) return st;
-    for (uint64_t q = 0; q < nq; ++q) resc += cnt[q * 4 + 3];
+    for (uint64_t q = 0; q < nq; ++q) resc += cnt[q * 4 + 3] + xcnt[q * 4 + 1];
     ctx->stats.rescored = resc;
     ctx->stats.d2h_bytes = d2h;
-    if (scores) {
-        // local (tile-sharded) order -> positions in the whole length-sorted database
-        for (uint64_t q = 0; q < nq; ++q)
-            for (uint64_t ls = 0; ls < n_pad; ++ls) {
-                const uint64_t g = ((ls / kTileSeqs) * ctx->num_shards + ctx->shard) * kTileSeqs + (ls % kTileSeqs);
-                if (g < ctx->n_total) scores[q * ctx->n_total + g] = local[q * n_pad + ls];
+    if (!local.empty()) {
+        const uint64_t ltiles = ctx->ntiles;
+        for (uint64_t q = 0; q < nq; ++q) {
+            int32_t *row = scores + q * ctx->n_total;
+            const int32_t *src = local.data() + q * n_pad;
+            for (uint64_t lt = 0; lt < ltiles; ++lt) {
+                const uint64_t g0 = (lt * ctx->num_shards + ctx->shard) * kTileSeqs;
+                if (g0 >= ctx->n_total) break;
+                memcpy(row + g0, src + lt * kTileSeqs, std::min<uint64_t>(kTileSeqs, ctx->n_total - g0) * sizeof(int32_t));
             }
+        }
     }
     return SWG_OK;
 }
@@ -1080,7 +1322,7 @@ int swg_gpu_debug_read(swg_ctx *ctx, const char *name, void *out, uint64_t max_b
     else if (!strcmp(name, "tile_cols")) { b = &ctx->d_tile_cols; n = (uint64_t)ctx->ntiles * sizeof(uint32_t); }
     else if (!strcmp(name, "profile")) { b = &ctx->d_profile; n = b->cap; }
     else if (!strcmp(name, "profile32")) { b = &ctx->d_profile32; n = b->cap; }
-    else if (!strcmp(name, "scores")) { b = &ctx->d_scores; n = ctx->q_count * ctx->ntiles * kTileSeqs * sizeof(int32_t); }
+    else if (!strcmp(name, "scores")) { b = &ctx->d_scores; n = ctx->run_window * ctx->ntiles * kTileSeqs * sizeof(int32_t); }
     else if (!strcmp(name, "counters")) { b = &ctx->d_counters; n = ctx->q_count * 4 * sizeof(uint32_t); }
     else return fail(ctx, SWG_ERR_ARG, "unknown buffer '%s'", name);
     *bytes = n;
@@ -1116,24 +1358,44 @@ int swimm_gpu_search_avx2_compat(char *query_sequences, unsigned short int *quer
 {
     (void)vect_sequences_db_blocks;
     (void)cpu_block_size;
-    (void)n_threads;
     const int vl = 32;
     if (!scores) return fail(nullptr, SWG_ERR_ARG, "scores is NULL");
-    swg_ctx *ctx = nullptr;
-    int st = swg_gpu_create(0, &ctx);
-    if (st != SWG_OK) return st;
+    // n_threads is read as the number of GPUs (0 or less: all visible ones)
+    int visible = 0;
+    cudaError_t ce = cudaGetDeviceCount(&visible);
+    if (ce != cudaSuccess) return cuda_fail(nullptr, ce, "cudaGetDeviceCount");
+    if (visible <= 0) return fail(nullptr, SWG_ERR_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
+    const int ngpu = n_threads <= 0 ? visible : std::min(n_threads, visible);
+    // every lane is searched; lanes that are pure padding have length 0 and score 0, as in the reference
     const uint64_t lanes = (uint64_t)vect_sequences_db_count * vl;
     std::vector<uint64_t> disp(vect_sequences_db_count + 1);
     for (uint64_t g = 0; g <= vect_sequences_db_count; ++g) disp[g] = vect_sequences_db_disp[g];
-    // every lane is searched; lanes that are pure padding have length 0 and score 0, as in the reference
-    st = swg_gpu_load_db_interleaved(ctx, (const signed char *)vect_sequences_db, vect_sequences_db_lengths,
-                                     vect_sequences_db_count, disp.data(), vl, lanes, 0, 1);
-    if (st == SWG_OK)
-        st = swg_gpu_search(ctx, (const signed char *)query_sequences, query_sequences_lengths, query_disp,
-                            query_sequences_count, (const signed char *)submat, open_gap, extend_gap, 0, scores, nullptr,
-                            workTime);
-    if (st != SWG_OK) snprintf(g_last_error, sizeof(g_last_error), "%s", ctx->err);
-    swg_gpu_destroy(ctx);
+    std::vector<uint16_t> lengths;
+    std::vector<signed char> flat;
+    deinterleave((const signed char *)vect_sequences_db, vect_sequences_db_lengths, disp.data(), vl, lanes, lengths, flat);
+    // one context per GPU, each with the tiles t % ngpu == g; all of them run at the same time, every fetch fills the
+    // score entries of its own shard
+    std::vector<swg_ctx *> ctxs((size_t)ngpu, nullptr);
+    int st = SWG_OK;
+    char err[512] = "";
+    for (int g = 0; g < ngpu && st == SWG_OK; ++g) {
+        st = swg_gpu_create(g, &ctxs[g]);
+        if (st == SWG_OK) st = swg_gpu_load_db(ctxs[g], lengths.data(), flat.data(), lanes, flat.size(), g, ngpu);
+        if (st == SWG_OK)
+            st = swg_gpu_set_queries(ctxs[g], (const signed char *)query_sequences, query_sequences_lengths, query_disp,
+                                     query_sequences_count, (const signed char *)submat, open_gap, extend_gap);
+        if (st == SWG_OK) st = swg_gpu_run(ctxs[g], 0, 1);
+        if (st != SWG_OK) snprintf(err, sizeof(err), "%s", ctxs[g] ? ctxs[g]->err : g_last_error);
+    }
+    double work = 0.0;
+    for (int g = 0; g < ngpu && st == SWG_OK; ++g) {
+        st = swg_gpu_fetch(ctxs[g], scores, nullptr);
+        if (st != SWG_OK) snprintf(err, sizeof(err), "%s", ctxs[g]->err);
+        work = std::max(work, ctxs[g]->stats.search_seconds);
+    }
+    for (int g = 0; g < ngpu; ++g) swg_gpu_destroy(ctxs[g]);
+    if (st != SWG_OK) snprintf(g_last_error, sizeof(g_last_error), "%s", err);
+    else if (workTime) *workTime = work;
     return st;
 }
 

@@ -176,6 +176,34 @@ Config wide_config(uint32_t m)
     return c;
 }
 
+// cycles one column costs a thread group on a busy SM: about 24 per row plus the per-column bookkeeping (measured on the
+// long-sequence workload); the serial chain of a sequence is its columns times this
+static double step_cycles(int K) { return 24.0 * K + 100.0; }
+
+double long_tile_limit(double seconds, int K, uint32_t passes)
+{
+    return 0.8 * seconds * kSmHz / (step_cycles(K) * passes);
+}
+
+XwConfig choose_xw_config(uint32_t m, double residues, double maxcols, long force_warps, long force_rows)
+{
+    XwConfig best;
+    if (m == 0) m = 1;
+    double best_cost = 1e300;
+    for (int W = 1; W <= 16; W *= 2)
+        for (int K = 1; K <= kMaxRowsPerThread; ++K) {
+            if ((force_warps && W != force_warps) || (force_rows && K != force_rows)) continue;
+            if ((uint32_t)(W * 32 * K) < m) continue;
+            if (W * ((K + 15) / 16) > 16) continue;                 // W passes of 12.5 KB (K <= 16) or 25 KB in shared memory
+            // throughput: the rows computed at the multi-pass rate of the sequence-pair kernel (same inner loop)
+            const double thr = (double)W * 32 * K / shape_rate(32, K, 2) * residues * 1e-9;
+            const double chain = (maxcols + 40.0 * W) * step_cycles(K) / kSmHz;
+            const double c = std::max(thr, chain) + 1e-3 * thr + 1e-3 * chain;
+            if (c < best_cost) { best_cost = c; best.K = K; best.W = W; }
+        }
+    return best;
+}
+
 // ---- the batch ------------------------------------------------------------------------------------
 void plan_batch(const std::vector<uint16_t> &q_len, const ShardShape &shard, const PlanOptions &opt,
                 std::vector<Config> &main_cfgs, std::vector<Config> &wide_cfgs, std::vector<WorkItem> &items)

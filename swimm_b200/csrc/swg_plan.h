@@ -20,6 +20,12 @@ struct Config {          // how one query is mapped onto thread groups
     bool global_profile;
 };
 
+struct XwConfig {        // how one query is mapped onto the long-sequence kernel (wavefront_xw.cuh)
+    int K = 0;           // rows per thread
+    int W = 0;           // warps (= concurrent passes of 32*K rows) per sequence pair; 0: the query does not fit (> 8192 rows)
+    bool ok() const { return W > 0; }
+};
+
 struct PairConfig {      // how a query pair is mapped onto the query-pair kernel (wavefront_q2.cuh)
     int G;
     std::vector<int> K;  // rows per thread of every pass (one launch per pass; a single-pass pair has one entry)
@@ -67,6 +73,13 @@ double q2_rate(int G, int K, bool multi);
 // sequence-pair kernel: shape for one query of m rows on this shard; the 32-thread shape of long tiles / 32-bit redo
 Config choose_config(uint32_t m, double residues, double maxcols, long force_group, long force_rows);
 Config wide_config(uint32_t m);
+
+// long-sequence kernel: W warps x 32 threads x K rows >= m with the profile of all W passes in shared memory; the shape
+// that minimises max(throughput time of `residues` residues, serial chain of a sequence of `maxcols` columns)
+XwConfig choose_xw_config(uint32_t m, double residues, double maxcols, long force_warps = 0, long force_rows = 0);
+// columns above which a sequence's serial chain (one column per step of K rows, `passes` times) would come close to a
+// launch that takes `seconds`: such tiles go to the long-sequence kernel
+double long_tile_limit(double seconds, int K, uint32_t passes);
 
 // query-pair kernel: launch heights covering m rows; the two lanes as streams of queries
 PairConfig choose_pair_config(uint32_t m, long force_group, long force_rows);

@@ -221,10 +221,12 @@ __global__ void __launch_bounds__(1024) bitonic_local_kernel(uint64_t *keys, uin
         if (base + i < npow2) keys[base + i] = s[i];
 }
 
-__global__ void emit_sorted_kernel(const uint64_t *keys, uint64_t top, uint64_t *out)
+// the scratch holds npow2 keys of THIS shard; `top` is clamped to the whole database, so on a sharded context it can
+// exceed them: the rest of the row is "no hit"
+__global__ void emit_sorted_kernel(const uint64_t *keys, uint64_t npow2, uint64_t top, uint64_t *out)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < top) { const uint64_t k = keys[i]; out[i] = k ? k - 1 : 0; }
+    if (i < top) { const uint64_t k = i < npow2 ? keys[i] : 0; out[i] = k ? k - 1 : 0; }
 }
 
 uint64_t pow2_at_least(uint64_t v)
@@ -289,7 +291,7 @@ cudaError_t launch_topk(const TopkPlan &pl, const int32_t *d_scores, uint64_t q_
             bitonic_local_kernel<<<(unsigned)(np2 / 2048), 1024, 0, stream>>>(d_scratch, np2, k, k);
             if (launches) *launches += 1;
         }
-        emit_sorted_kernel<<<(unsigned)((pl.top + 255) / 256), 256, 0, stream>>>(d_scratch, pl.top, d_out + q * pl.top);
+        emit_sorted_kernel<<<(unsigned)((pl.top + 255) / 256), 256, 0, stream>>>(d_scratch, np2, pl.top, d_out + q * pl.top);
         if (launches) *launches += 1;
     }
     return cudaGetLastError();

@@ -325,14 +325,12 @@ cudaError_t launch_wf_l32_gp(int grid, cudaStream_t stream, const WfParams &p);
 template <class L, int G, int K, bool MP, bool GP, int GOE = 0, int GE = 0>
 cudaError_t launch_one(int grid, size_t smem, cudaStream_t stream, const WfParams &p)
 {
-    static size_t configured[64] = {0};            // per device: the attribute lives in the device's context
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (smem > configured[dev & 63]) {
+    // the attribute lives in the device's context; setting it on every launch is a cheap driver call and keeps the
+    // launcher free of shared state (one context per host thread is allowed)
+    if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(wavefront_kernel<L, G, K, MP, GP, GOE, GE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[dev & 63] = smem;
     }
     wavefront_kernel<L, G, K, MP, GP, GOE, GE><<<grid, kBlockThreads, smem, stream>>>(p);
     return cudaGetLastError();

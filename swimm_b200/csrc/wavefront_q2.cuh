@@ -263,15 +263,10 @@ cudaError_t launch_q2_g32_last(int K, int grid, cudaStream_t stream, const WfPar
 template <int G, int K, bool CIN, bool COUT, int GOE = 0, int GE = 0>
 cudaError_t launch_q2_one(int grid, cudaStream_t stream, const WfParams &p)
 {
-    static bool configured[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(wavefront_q2_kernel<G, K, CIN, COUT, GOE, GE>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kQ2ProfileBytes);
-        if (e != cudaSuccess) return e;
-        configured[dev & 63] = true;
-    }
+    // set on every launch (cheap, and no state shared between host threads driving different GPUs)
+    cudaError_t e = cudaFuncSetAttribute(wavefront_q2_kernel<G, K, CIN, COUT, GOE, GE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kQ2ProfileBytes);
+    if (e != cudaSuccess) return e;
     wavefront_q2_kernel<G, K, CIN, COUT, GOE, GE><<<grid, kBlockThreads, kQ2ProfileBytes, stream>>>(p);
     return cudaGetLastError();
 }

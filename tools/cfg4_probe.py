@@ -19,10 +19,13 @@ b62 = host.submat("blosum62")
 s = gpu.GpuSearch(0)
 s.load_db(dl, dc)
 ref = None
-for name, opts in [("auto", {}), ("no long path", {"long_threshold": 65535}), ("all long", {"long_threshold": 8}),
-                   ("pairs forced", {"query_pairing": 2}), ("no pairs", {"query_pairing": 0}),
-                   ("no pairs, no long", {"query_pairing": 0, "long_threshold": 65535})]:
-    for k, v in {"long_threshold": 0, "query_pairing": 1}.items():
+for name, opts in [("auto", {}), ("auto verbose", {"verbose": 1}), ("old long kernel", {"long_kernel": 0}),
+                   ("no long path", {"long_threshold": 65535}),
+                   ("all long (xw)", {"long_threshold": 8}), ("all long W16", {"long_threshold": 8, "xw_warps": 16}),
+                   ("all long W8", {"long_threshold": 8, "xw_warps": 8}), ("all long W4", {"long_threshold": 8, "xw_warps": 4}),
+                   ("long > 20000", {"long_threshold": 20000}), ("long > 30000", {"long_threshold": 30000}),
+                   ("no pairs", {"query_pairing": 0}), ("no pairs, old long", {"query_pairing": 0, "long_kernel": 0})]:
+    for k, v in {"long_threshold": 0, "query_pairing": 1, "long_kernel": 1, "xw_warps": 0, "verbose": 0}.items():
         s.set_option(k, v)
     for k, v in opts.items():
         s.set_option(k, v)
