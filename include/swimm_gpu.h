@@ -100,9 +100,23 @@ int swg_gpu_search(swg_ctx *ctx, const signed char *queries, const uint16_t *q_l
  * that the kernels can be timed with the inputs already resident in HBM */
 int swg_gpu_set_queries(swg_ctx *ctx, const signed char *queries, const uint16_t *q_lengths, const uint32_t *q_disp,
                         uint64_t q_count, const signed char *submat, int open_gap, int extend_gap);   /* H2D */
+/* keep_scores != 0: every query's score row stays on the device for swg_gpu_fetch(scores != NULL).  0: only hit lists
+ * are wanted; the run may then search the batch in chunks of queries so that its score rows fit option
+ * "score_budget_mb" (fetching scores after such a run returns SWG_ERR_STATE). */
 int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores);     /* enqueue all kernels; returns immediately */
 int swg_gpu_fetch(swg_ctx *ctx, int32_t *scores, uint64_t *top_keys);   /* wait + D2H */
 int swg_gpu_sync(swg_ctx *ctx);                                   /* wait only */
+
+/* ---- streaming: keep the database resident and feed batches as they arrive (replaces the one-shot flow of
+ * swimm.c:38-160 for a long-lived process) ----
+ * swg_gpu_submit enqueues the upload of a batch (copy stream), all its kernels and the download of its hit lists, and
+ * returns at once with a ticket.  Two batches may be in flight: while batch k computes, batch k+1 is uploaded and its
+ * launches queue up behind, so the GPU does not idle between batches.  swg_gpu_poll hands a finished batch's hit lists
+ * out (wait != 0: blocks until it is finished); *done = 1 when they were delivered.  top_keys: [q_count][top] as in
+ * swg_gpu_search; device_seconds (may be NULL): CUDA-event time from the batch's first kernel to its last download. */
+int swg_gpu_submit(swg_ctx *ctx, const signed char *queries, const uint16_t *q_lengths, const uint32_t *q_disp,
+                   uint64_t q_count, const signed char *submat, int open_gap, int extend_gap, uint64_t top, int *ticket);
+int swg_gpu_poll(swg_ctx *ctx, int ticket, int wait, uint64_t *top_keys, double *device_seconds, int *done);
 
 int swg_gpu_get_stats(swg_ctx *ctx, swg_stats *out);
 /* device time (CUDA events) of each query's kernels in the last completed run, in the order the queries were given */
@@ -129,7 +143,11 @@ int swg_gpu_pipebench(swg_ctx *ctx, int max_probes, double *ginstr_per_s, double
  * "profile32", "scores", "counters"}; *bytes receives the buffer's size, at most max_bytes are copied. */
 int swg_gpu_debug_read(swg_ctx *ctx, const char *name, void *out, uint64_t max_bytes, uint64_t *bytes);
 
-/* tuning knobs (all optional): name in {"long_threshold", "force_group", "force_rows", "block_threads",
+/* tuning knobs (all optional): name in {"long_threshold" (0 default: the long-tile threshold is estimated per query
+ * from the run times; > 0: tiles with more columns than this run the long-sequence kernel), "long_kernel" (1 default:
+ * long tiles run the cross-warp wavefront kernel; 0: the 32-thread shape of the sequence-pair kernel), "xw_warps",
+ * "xw_rows" (forced shape of the long-sequence kernel), "score_budget_mb" (bytes of score rows a run may hold when only
+ * hit lists are wanted, default 4096: larger batches are searched in chunks of queries), "force_group", "force_rows", "block_threads",
  * "query_pairing" (0 never / 1 planner / 2 always pair the queries of a batch for the query-pair kernel),
  * "q2_group", "q2_rows" (forced shape of the query-pair kernel), "grid_blocks" (CTAs per search launch, 0 = one per SM),
  * "pass_lines" (1 default; 0 = never allocate the query-pair kernel's pass lines, 8 bytes per database column:
@@ -138,7 +156,8 @@ int swg_gpu_debug_read(swg_ctx *ctx, const char *name, void *out, uint64_t max_b
 int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value);
 
 /* Drop-in with the reference signature (CPUsearch.h:37-39).  n_threads is read as the number of GPUs
- * to use (0 = all), cpu_block_size is ignored.  Fills scores[q*vect_count*vector_length + s] for every
+ * to use (0 or less = all visible; more than visible = all visible): the database is sharded over them by tiles and
+ * every GPU fills its own entries of `scores`.  cpu_block_size is ignored.  Fills scores[q*vect_count*vector_length + s] for every
  * lane (padded lanes get 0) and *workTime, exactly as cpu_search_avx2_sp does.  vector_length is 32. */
 int swimm_gpu_search_avx2_compat(char *query_sequences, unsigned short int *query_sequences_lengths,
                                  unsigned long int query_sequences_count, unsigned int *query_disp,

@@ -26,7 +26,6 @@ namespace {
 
 constexpr uint32_t kDefaultLongCols = 0;       // 0: the long-tile threshold is estimated per query / launch
 constexpr uint64_t kMaxLongBlocks = 12;
-constexpr uint32_t kXwRingCols = 1024;         // entries of a warp's last-row ring in the long-sequence kernel
 
 struct DeviceBuf {
     void *p = nullptr;
@@ -82,14 +81,31 @@ struct swg_ctx {
     std::vector<uint16_t> q_len;
     std::vector<uint32_t> q_off;     // offsets into d_queries
     int open_gap = 10, extend_gap = 2;
+    // the buffer set of a batch (swapped with a slot's by swg_gpu_submit): queries + matrix on the device, the pinned
+    // staging they are uploaded from, the hit lists, and the two events that guard their reuse
     DeviceBuf d_queries, d_submat;
     char *h_stage = nullptr;         // pinned staging of the query upload
     size_t h_stage_cap = 0;
+    cudaEvent_t ev_upload = nullptr;     // recorded on copy_stream when the upload from h_stage has completed
+    cudaEvent_t ev_bufs_free = nullptr;  // recorded on stream behind the last run that read d_queries / wrote d_top_out
+    cudaStream_t copy_stream = nullptr;
+    struct QuerySlot {
+        DeviceBuf d_queries, d_submat, d_top_out;
+        char *h_stage = nullptr;
+        size_t h_stage_cap = 0;
+        cudaEvent_t ev_upload = nullptr, ev_bufs_free = nullptr, ev_begin = nullptr, ev_done = nullptr;
+        uint64_t *h_keys = nullptr;      // pinned: the batch's hit lists, [q_count][top]
+        size_t h_keys_cap = 0;
+        bool busy = false;
+        int ticket = -1;
+        uint64_t q_count = 0, top = 0, top_stride = 0;
+    } slots[2];
+    int next_ticket = 0;
 
     // work buffers
     DeviceBuf d_scores, d_profile, d_profile32, d_boundary, d_counters, d_resc_list, d_topk_scratch, d_top_out;
     DeviceBuf d_profile_q2, d_lines, d_resc_list2, d_q2_counters;
-    DeviceBuf d_profile_xw, d_xw_ring, d_xw_counters, d_xw_list;     // long-sequence kernel (wavefront_xw.cuh)
+    DeviceBuf d_profile_xw, d_xw_counters, d_xw_list;     // long-sequence kernel (wavefront_xw.cuh)
     std::vector<WorkItem> items;            // schedule of the last run
     std::vector<cudaEvent_t> item_events;   // items.size() + 1 marks
     std::vector<cudaEvent_t> chunk_events;  // two per chunk of queries, around its top-r selection
@@ -310,6 +326,15 @@ int swg_gpu_create(int device, swg_ctx **out)
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_lo);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_bufs_free, cudaEventDisableTiming);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&ctx->slots[k].ev_upload, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slots[k].ev_bufs_free, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->slots[k].ev_begin);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->slots[k].ev_done);
+    }
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_end);
     if (e != cudaSuccess) {
@@ -325,9 +350,23 @@ void swg_gpu_destroy(swg_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_db(ctx);
+    for (int k = 0; k < 2; ++k) {
+        swg_ctx::QuerySlot &sl = ctx->slots[k];
+        sl.d_queries.release();
+        sl.d_submat.release();
+        sl.d_top_out.release();
+        if (sl.h_stage) cudaFreeHost(sl.h_stage);
+        if (sl.h_keys) cudaFreeHost(sl.h_keys);
+        for (cudaEvent_t ev : {sl.ev_upload, sl.ev_bufs_free, sl.ev_begin, sl.ev_done})
+            if (ev) cudaEventDestroy(ev);
+    }
+    if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
+    if (ctx->ev_bufs_free) cudaEventDestroy(ctx->ev_bufs_free);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     ctx->d_queries.release();
     ctx->d_submat.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -343,7 +382,6 @@ void swg_gpu_destroy(swg_ctx *ctx)
     ctx->d_resc_list2.release();
     ctx->d_q2_counters.release();
     ctx->d_profile_xw.release();
-    ctx->d_xw_ring.release();
     ctx->d_xw_counters.release();
     ctx->d_xw_list.release();
     for (cudaEvent_t ev : ctx->q_events) cudaEventDestroy(ev);
@@ -627,13 +665,19 @@ int swg_gpu_set_queries(swg_ctx *ctx, const signed char *queries, const uint16_t
             SWG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_stage, need + need / 2));
             ctx->h_stage_cap = need + need / 2;
         }
-        SWG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // a previous upload may still read the staging buffer
+        SWG_CUDA(ctx, cudaEventSynchronize(ctx->ev_upload));     // the previous upload from this staging buffer is complete
         for (uint64_t i = 0; i < q_count; ++i)
             if (q_lengths[i]) memcpy(ctx->h_stage + ctx->q_off[i], queries + q_disp[i], q_lengths[i]);
         memcpy(ctx->h_stage + total, submat, 768);
         SWG_CUDA(ctx, ctx->d_queries.reserve(need));
-        SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_queries.p, ctx->h_stage, need, cudaMemcpyHostToDevice, ctx->stream));
-        SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_submat.p, ctx->d_queries.as<char>() + total, 768, cudaMemcpyDeviceToDevice, ctx->stream));
+        // the upload runs on the copy stream, behind the last run that read this buffer set and ahead of the next one
+        // (with swg_gpu_submit's two sets it overlaps the kernels of the batch in flight)
+        SWG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_bufs_free, 0));
+        SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_queries.p, ctx->h_stage, need, cudaMemcpyHostToDevice, ctx->copy_stream));
+        SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_submat.p, ctx->d_queries.as<char>() + total, 768, cudaMemcpyDeviceToDevice,
+                                      ctx->copy_stream));
+        SWG_CUDA(ctx, cudaEventRecord(ctx->ev_upload, ctx->copy_stream));
+        SWG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_upload, 0));
     }
     ctx->open_gap = open_gap;
     ctx->extend_gap = extend_gap;
@@ -805,7 +849,6 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     }
     if (any_xw) {
         SWG_CUDA(ctx, ctx->d_profile_xw.reserve((size_t)16 * kPassBytes));
-        SWG_CUDA(ctx, ctx->d_xw_ring.reserve((size_t)ctx->sm_count * 16 * kXwRingCols * sizeof(uint2)));
         SWG_CUDA(ctx, ctx->d_xw_list.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
     }
     const TopkPlan tp = topk_plan(n_pad, top, window);
@@ -843,8 +886,6 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             if (!xc.ok()) return;
             w.profile = ctx->d_profile_xw.as<uint8_t>();
             w.xw_warps = (uint32_t)xc.W;
-            w.xw_ring_cols = kXwRingCols;
-            w.xw_ring = ctx->d_xw_ring.as<uint2>();
             if (we == cudaSuccess && fresh((2u << 20) + (uint32_t)xc.K)) we = launch_xw_l16(xc.K, 1, ctx->stream, w);
             if (we == cudaSuccess && fresh((3u << 20) + (uint32_t)xc.K)) we = launch_xw_l32(xc.K, 1, ctx->stream, w);
         };
@@ -952,8 +993,6 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         x.resc_count = xcnt + 1;
         x.resc_list = ctx->d_xw_list.as<uint32_t>();
         x.xw_warps = (uint32_t)xc.W;
-        x.xw_ring_cols = kXwRingCols;
-        x.xw_ring = ctx->d_xw_ring.as<uint2>();
         e = launch_xw_l16(xc.K, xgrid, st, x);
         x.task_counter = xcnt + 2;
         if (e == cudaSuccess) e = launch_xw_l32(xc.K, xgrid, st, x);
@@ -1158,6 +1197,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     ctx->stats.padded_cells = padded;
     if (!ctx->ntiles && nq * top) SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_top_out.p, 0, nq * top * sizeof(uint64_t), ctx->stream));
     SWG_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
+    SWG_CUDA(ctx, cudaEventRecord(ctx->ev_bufs_free, ctx->stream));
     ctx->run_done = true;
     return SWG_OK;
 }
@@ -1262,6 +1302,87 @@ int swg_gpu_search(swg_ctx *ctx, const signed char *queries, const uint16_t *q_l
     if (st == SWG_OK) st = swg_gpu_fetch(ctx, scores, top_keys);
     if (st == SWG_OK && work_seconds) *work_seconds = ctx->stats.search_seconds;
     return st;
+}
+
+// ---- streaming: two batches in flight ----------------------------------------------------------------
+static void swap_slot(swg_ctx *ctx, swg_ctx::QuerySlot &sl)
+{
+    std::swap(ctx->d_queries, sl.d_queries);
+    std::swap(ctx->d_submat, sl.d_submat);
+    std::swap(ctx->d_top_out, sl.d_top_out);
+    std::swap(ctx->h_stage, sl.h_stage);
+    std::swap(ctx->h_stage_cap, sl.h_stage_cap);
+    std::swap(ctx->ev_upload, sl.ev_upload);
+    std::swap(ctx->ev_bufs_free, sl.ev_bufs_free);
+}
+
+int swg_gpu_submit(swg_ctx *ctx, const signed char *queries, const uint16_t *q_lengths, const uint32_t *q_disp,
+                   uint64_t q_count, const signed char *submat, int open_gap, int extend_gap, uint64_t top, int *ticket)
+{
+    if (!ctx || !ticket) return fail(ctx, SWG_ERR_ARG, "NULL argument");
+    swg_ctx::QuerySlot &sl = ctx->slots[ctx->next_ticket & 1];
+    if (sl.busy) return fail(ctx, SWG_ERR_STATE, "two batches are in flight: poll ticket %d first", sl.ticket);
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    swap_slot(ctx, sl);                  // the batch uses the slot's buffer set
+    int st = swg_gpu_set_queries(ctx, queries, q_lengths, q_disp, q_count, submat, open_gap, extend_gap);
+    cudaError_t e = cudaSuccess;
+    if (st == SWG_OK) e = cudaEventRecord(sl.ev_begin, ctx->stream);
+    if (st == SWG_OK && e == cudaSuccess) st = swg_gpu_run(ctx, top, 0);
+    const uint64_t n_keys = q_count * ctx->run_top;
+    if (st == SWG_OK && e == cudaSuccess && n_keys > sl.h_keys_cap) {
+        if (sl.h_keys) cudaFreeHost(sl.h_keys);
+        sl.h_keys = nullptr;
+        sl.h_keys_cap = 0;
+        e = cudaMallocHost((void **)&sl.h_keys, (n_keys + n_keys / 2) * sizeof(uint64_t));
+        if (e == cudaSuccess) sl.h_keys_cap = n_keys + n_keys / 2;
+    }
+    if (st == SWG_OK && e == cudaSuccess && n_keys)
+        e = cudaMemcpyAsync(sl.h_keys, ctx->d_top_out.p, n_keys * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (st == SWG_OK && e == cudaSuccess) e = cudaEventRecord(sl.ev_done, ctx->stream);
+    if (st == SWG_OK && e == cudaSuccess) e = cudaEventRecord(ctx->ev_bufs_free, ctx->stream);     // behind the download
+    swap_slot(ctx, sl);
+    ctx->run_done = false;               // the legacy fetch must not read another batch's buffers
+    ctx->queries_ready = false;
+    if (st != SWG_OK) return st;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "swg_gpu_submit");
+    sl.busy = true;
+    sl.ticket = ctx->next_ticket++;
+    sl.q_count = q_count;
+    sl.top = ctx->run_top;
+    sl.top_stride = ctx->run_top_stride;
+    ctx->stats.h2d_bytes = ctx->q_off[q_count] + 768;
+    ctx->stats.d2h_bytes = n_keys * sizeof(uint64_t);
+    *ticket = sl.ticket;
+    return SWG_OK;
+}
+
+int swg_gpu_poll(swg_ctx *ctx, int ticket, int wait, uint64_t *top_keys, double *device_seconds, int *done)
+{
+    if (!ctx || !done) return fail(ctx, SWG_ERR_ARG, "NULL argument");
+    *done = 0;
+    swg_ctx::QuerySlot &sl = ctx->slots[ticket & 1];
+    if (ticket < 0 || !sl.busy || sl.ticket != ticket) return fail(ctx, SWG_ERR_STATE, "ticket %d is not in flight", ticket);
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (wait) SWG_CUDA(ctx, cudaEventSynchronize(sl.ev_done));
+    else {
+        const cudaError_t q = cudaEventQuery(sl.ev_done);
+        if (q == cudaErrorNotReady) return SWG_OK;
+        if (q != cudaSuccess) return cuda_fail(ctx, q, "cudaEventQuery");
+    }
+    if (top_keys && sl.top_stride) {
+        // rows of the caller's array are top_stride keys apart; the batch produced min(top, n) keys per query
+        if (sl.top != sl.top_stride) memset(top_keys, 0, sl.q_count * sl.top_stride * sizeof(uint64_t));
+        for (uint64_t q = 0; q < sl.q_count && sl.top; ++q)
+            memcpy(top_keys + q * sl.top_stride, sl.h_keys + q * sl.top, sl.top * sizeof(uint64_t));
+    }
+    if (device_seconds) {
+        float ms = 0.f;
+        SWG_CUDA(ctx, cudaEventElapsedTime(&ms, sl.ev_begin, sl.ev_done));
+        *device_seconds = ms * 1e-3;
+    }
+    sl.busy = false;
+    *done = 1;
+    return SWG_OK;
 }
 
 int swg_gpu_get_stats(swg_ctx *ctx, swg_stats *out)

@@ -10,7 +10,7 @@
 // Here the query's rows are tiled into W passes of 32*K rows and the W passes of a sequence run CONCURRENTLY, one per
 // warp: warp w of a group owns rows [w*32*K, (w+1)*32*K); inside the warp the columns stream through the 32 threads
 // as in wavefront.cuh (systolic pipeline, H diagonal term and E in registers, DS one column ahead).  The last row
-// (H, F) of warp w's pass leaves its thread 31 one column at a time into a ring in global memory (L2 resident) and
+// (H, F) of warp w's pass leaves its thread 31 one column at a time into a 128-entry ring in shared memory and
 // enters warp w+1's thread 0 forty steps later: the tiles (pass, 4-column trip) of one sequence form a wavefront over
 // the warps, 40 columns apart.  A sequence of n columns therefore takes n + 40*W steps instead of n * W, and a group
 // is busy on a sequence for 1/W of the time -- the database's longest sequence stops bounding the launch.
@@ -42,7 +42,8 @@ namespace swg {
 
 constexpr int kXwTaskRing = 32;            // tasks the first warp of a group may be ahead of the last one
 constexpr uint32_t kXwLag = 40;            // steps a warp stays behind the warp above it (32 threads + 2 trips)
-constexpr uint32_t kXwRingGuard = 64;      // ring entries kept between a writer and the reader's oldest live entry
+constexpr uint32_t kXwRing = 128;          // entries of a warp's last-row ring (shared memory, 8 bytes each)
+constexpr uint32_t kXwRingGuard = 8;       // margin of the overwrite test (an entry is dead 34 steps before the test needs it)
 constexpr uint32_t kXwDone = 0xffffffffu;  // published step count of a warp that has left the kernel
 constexpr int kXwMaxRows = 8192;           // longest query the shapes cover
 
@@ -112,8 +113,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_xw_kernel(const Wf
     const uint32_t w = warp % W;                      // this warp's pass
     const uint32_t grp = warp / W;
     const bool has_in = w > 0, has_out = w + 1 < W;
-    const uint32_t R = p.xw_ring_cols, rmask = R - 1;
-    uint2 *const ring_out = p.xw_ring + ((size_t)blockIdx.x * 16 + warp) * R;
+    // the last-row rings live behind the profile: no long-latency load is ever outstanding when a step count is
+    // published (the release store's fence would wait for it)
+    constexpr uint32_t R = kXwRing, rmask = R - 1;
+    uint2 *const ring_out = reinterpret_cast<uint2 *>(prof_smem + W * SLICE) + warp * R;
     const uint2 *const ring_in = ring_out - R;        // the ring of the warp above (has_in)
     const uint32_t *const flag_prev = &s_prog[warp - (has_in ? 1 : 0)];
     const uint32_t *const flag_next = &s_prog[warp + (has_out ? 1 : 0)];
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_xw_kernel(const Wf
         }
         out_h = hp;
         out_f = f;
-        if (store_on) __stcg(ring_out + store_at, make_uint2((uint32_t)out_h, (uint32_t)out_f));
+        if (store_on) ring_out[store_at] = make_uint2((uint32_t)out_h, (uint32_t)out_f);
         if (HEAD && (pkn & kMarkSegment)) {          // the next column starts a new task
 #pragma unroll
             for (int x = 0; x < K; ++x) { DS[x] = score_of(x); E[x] = L::splat(0); }
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_xw_kernel(const Wf
     // ---- the stream of columns ----
     // `base` = steps this warp has completed before the current segment.  In step S thread 0 processes stream column
     // S - 1 (its word arrived in step S - 1), thread 31 processes and parks column S - 32, and the (H, F) entering
-    // column S + 3 is loaded (a queue of four register pairs hides the L2 round trip).
+    // column S + 3 is loaded into a queue of four register pairs.
     uint32_t base = 0, prod_seen = 0, cons_seen = 0;
     uint2 ring[NC];
 #pragma unroll
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_xw_kernel(const Wf
     if (has_in) {
         prod_seen = wait_at_least(flag_prev, kXwLag - NC);
 #pragma unroll
-        for (int j = 1; j < NC; ++j) ring[j] = __ldcg(ring_in + (j - 1));
+        for (int j = 1; j < NC; ++j) ring[j] = ring_in[j - 1];
     }
     bool pending = false;
     uint32_t pend_lseq = 0;
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_xw_kernel(const Wf
                 const bool first = decltype(head_tag)::value && j == 0 && trip == 0;
                 const uint32_t pkn = prmt(word, first ? kMarkSegment : 0u, (j & 1) ? selB : selA);
                 const uint2 hf = ring[j];
-                if (has_in) ring[j] = __ldcg(ring_in + ((S0 + j + NC - 1) & rmask));
+                if (has_in) ring[j] = ring_in[(S0 + j + NC - 1) & rmask];
                 column(head_tag, pkn, hf, (S0 + j - G) & rmask);
             }
             wd = nw;
@@ -337,8 +340,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_xw_kernel(const Wf
 cudaError_t launch_xw_l16(int K, int grid, cudaStream_t stream, const WfParams &p);
 cudaError_t launch_xw_l32(int K, int grid, cudaStream_t stream, const WfParams &p);
 
-// dynamic shared memory of a shape: the compact profile of W passes
-inline size_t xw_smem_bytes(int K, int W) { return (size_t)W * kLetters * (size_t)((K + 15) / 16) * 512; }
+// dynamic shared memory of a shape: the compact profile of W passes + one last-row ring per warp
+inline size_t xw_smem_bytes(int K, int W)
+{
+    return (size_t)W * kLetters * (size_t)((K + 15) / 16) * 512 + 16 * (size_t)kXwRing * sizeof(uint2);
+}
 
 template <class L, int K, int GOE = 0, int GE = 0>
 cudaError_t launch_xw_one(int grid, cudaStream_t stream, const WfParams &p)

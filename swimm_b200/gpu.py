@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "swg_gpu_load_db_shard", "swg_gpu_load_db_interleaved", "swg_gpu_db_local_sequences", "swg_gpu_db_local_residues", "swg_gpu_search",
     "swg_gpu_set_queries", "swg_gpu_run", "swg_gpu_fetch", "swg_gpu_sync", "swg_gpu_get_stats", "swg_gpu_get_query_seconds",
     "swg_gpu_get_query_kernels", "swg_plan_describe", "swg_gpu_pipebench",
-    "swg_gpu_set_option", "swg_gpu_debug_read", "swimm_gpu_search_avx2_compat",
+    "swg_gpu_set_option", "swg_gpu_debug_read", "swimm_gpu_search_avx2_compat", "swg_gpu_submit", "swg_gpu_poll",
 ]
 
 
@@ -74,6 +74,8 @@ def load_library() -> C.CDLL:
     L.swg_gpu_pipebench.argtypes = [vp, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.swg_gpu_debug_read.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     L.swg_gpu_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.swg_gpu_submit.argtypes = [vp, vp, vp, vp, u64, vp, i32, i32, u64, C.POINTER(i32)]
+    L.swg_gpu_poll.argtypes = [vp, i32, i32, vp, C.POINTER(C.c_double), C.POINTER(i32)]
     L.swimm_gpu_search_avx2_compat.argtypes = [vp, vp, C.c_ulong, vp, vp, vp, vp, C.c_ulong, vp, vp, i32, i32, i32, i32,
                                                vp, C.POINTER(C.c_double)]
     for f in ABI_SYMBOLS:
@@ -210,6 +212,31 @@ class GpuSearch:
         self.set_queries(q_codes, q_lengths, q_disp, submat, go, ge)
         self.run(top, want_scores)
         return self.fetch(want_scores, top > 0)
+
+    def submit(self, q_codes, q_lengths, q_disp, submat, go, ge, top) -> int:
+        """Streaming: enqueue a whole batch (upload, kernels, hit-list download) and return a ticket at once; two
+        batches may be in flight."""
+        q_codes = np.ascontiguousarray(q_codes, dtype=np.int8)
+        q_lengths = np.ascontiguousarray(q_lengths, dtype=np.uint16)
+        q_disp = np.ascontiguousarray(q_disp, dtype=np.uint32)
+        submat = np.ascontiguousarray(submat, dtype=np.int8)
+        t = C.c_int(-1)
+        self._check(self.L.swg_gpu_submit(self.ctx, q_codes.ctypes.data, q_lengths.ctypes.data, q_disp.ctypes.data,
+                                          len(q_lengths), submat.ctypes.data, go, ge, int(top), C.byref(t)), "submit")
+        self._tickets = getattr(self, "_tickets", {})
+        self._tickets[t.value] = (len(q_lengths), int(top))
+        return t.value
+
+    def poll(self, ticket: int, wait: bool = True, keys_out: np.ndarray | None = None):
+        """-> (hit keys [q][top] or None when not finished, device seconds)."""
+        nq, top = self._tickets[ticket]
+        keys = keys_out if keys_out is not None else np.zeros((nq, top), dtype=np.uint64)
+        done, secs = C.c_int(0), C.c_double(0)
+        self._check(self.L.swg_gpu_poll(self.ctx, ticket, int(wait), keys.ctypes.data, C.byref(secs), C.byref(done)), "poll")
+        if not done.value:
+            return None, 0.0
+        del self._tickets[ticket]
+        return keys, secs.value
 
     def stats(self) -> dict:
         s = Stats()

@@ -1,0 +1,134 @@
+"""Batch handling of the CUDA library through the C ABI: score-row window (large batches searched in chunks of queries),
+streaming submit / poll with two batches in flight, sharded full-sort top-r, multi-GPU reference-signature entry."""
+import numpy as np
+import pytest
+
+from swimm_b200 import host, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "gpu-marked test collected without a CUDA device"
+    from swimm_b200 import gpu as g
+    s = g.GpuSearch(0)
+    yield s
+    s.close()
+
+
+def _db(seed, n, hi=900):
+    rng = np.random.default_rng(seed)
+    db = synth.make_seqset(rng, synth.lognormal_lengths(rng, n, 4.6, 0.7, 1, hi))
+    _, dl, dc = synth.length_sorted(db)
+    do = np.zeros(db.n + 1, np.uint64)
+    np.cumsum(dl.astype(np.uint64), out=do[1:])
+    return db, dl, dc, do
+
+
+def _queries(seed, lens, db=None):
+    rng = np.random.default_rng(seed)
+    q = synth.make_queries(rng, lens)
+    if db is not None:
+        synth.plant(rng, db, q, fraction=0.05, frag_range=(5, 200), rate=0.1)
+    _, ql, qc = synth.length_sorted(q)
+    qo = np.zeros(q.n + 1, np.uint32)
+    np.cumsum(ql.astype(np.uint32), out=qo[1:])
+    return ql, qc, qo
+
+
+def _check_keys(oracle, want, keys, top):
+    from swimm_b200.gpu import split_key
+    for qi in range(want.shape[0]):
+        ts, ti = oracle.top(want[qi], top)
+        ks, ki = split_key(keys[qi])
+        assert np.array_equal(ki, ti.astype(np.int64)) and np.array_equal(ks, ts), qi
+
+
+def test_score_window_chunks_match_one_piece(gpu, oracle):
+    """37 queries with a 1 MB score budget on a 3000-sequence shard: 12 KB per row -> the batch is searched in several
+    chunks of queries (each planned, paired and top-r-selected on its own); hit lists equal the oracle's, and a fetch of
+    score rows after such a run is refused."""
+    from swimm_b200.gpu import SwgError
+    db, dl, dc, do = _db(3, 3000)
+    lens = list(np.random.default_rng(4).integers(20, 1400, 37))
+    ql, qc, qo = _queries(5, lens, db)
+    _, dl, dc = synth.length_sorted(db)
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    gpu.load_db(dl, dc)
+    gpu.set_option("score_budget_mb", 1)
+    try:
+        _, keys = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 15)
+        _check_keys(oracle, want, keys, 15)
+        launches_chunked = gpu.stats()["launches"]
+        with pytest.raises(SwgError):
+            gpu.fetch(True, False)
+        # the full score vectors are still available on request (keep_scores): one piece, whatever the budget
+        got, keys2 = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 15, want_scores=True)
+        assert np.array_equal(got, want) and np.array_equal(keys2, keys)
+        assert launches_chunked > gpu.stats()["launches"]          # more chunks -> more (smaller) groups and selections
+    finally:
+        gpu.set_option("score_budget_mb", 4096)
+
+
+def test_submit_poll_two_batches_in_flight(gpu, oracle):
+    """Streaming: three batches through one resident database, the next one submitted before the previous is polled;
+    a third submit without a poll is refused; results equal the blocking call's and the oracle's."""
+    from swimm_b200.gpu import SwgError
+    db, dl, dc, do = _db(11, 2500)
+    batches = [_queries(20 + i, lens, db) for i, lens in enumerate([[40, 144, 333], [1200, 2100], [5, 77, 600, 601, 999]])]
+    _, dl, dc = synth.length_sorted(db)
+    gpu.load_db(dl, dc)
+    b62 = host.submat("blosum62")
+    t0 = gpu.submit(batches[0][1], batches[0][0], batches[0][2][:-1], b62, 10, 2, 12)
+    t1 = gpu.submit(batches[1][1], batches[1][0], batches[1][2][:-1], b62, 10, 2, 12)
+    with pytest.raises(SwgError):
+        gpu.submit(batches[2][1], batches[2][0], batches[2][2][:-1], b62, 10, 2, 12)
+    k0, s0 = gpu.poll(t0)
+    t2 = gpu.submit(batches[2][1], batches[2][0], batches[2][2][:-1], b62, 10, 2, 12)
+    k1, s1 = gpu.poll(t1)
+    k2, s2 = gpu.poll(t2)
+    assert s0 > 0 and s1 > 0 and s2 > 0
+    for (ql, qc, qo), keys in zip(batches, [k0, k1, k2]):
+        want = oracle.search(qc, qo, dc, do, b62, 10, 2)
+        _check_keys(oracle, want, keys, 12)
+        _, blocking = gpu.search(qc, ql, qo[:-1], b62, 10, 2, 12)
+        assert np.array_equal(blocking, keys)
+
+
+@pytest.mark.parametrize("shards", [2, 5])
+def test_sharded_full_sort_top_beyond_local_count(gpu, oracle, shards):
+    """`-r <n>` on a sharded context: top is clamped to the whole database, which exceeds what one shard holds (the
+    full-sort path then has fewer keys than `top`: the rest of the row must read as "no hit", not as scratch memory)."""
+    from swimm_b200.gpu import merge_top_keys
+    db, dl, dc, do = _db(31, 3100, hi=300)
+    ql, qc, qo = _queries(32, [60, 200], db)
+    _, dl, dc = synth.length_sorted(db)
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    top = db.n                           # > 2048: full sort; > the shard's padded count
+    parts = []
+    for s in range(shards):
+        gpu.load_db(dl, dc, shard=s, num_shards=shards)
+        _, keys = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, top)
+        local = gpu.local_sequences
+        assert (keys[:, local:] == 0).all(), "keys beyond the shard's sequences must be empty"
+        parts.append(keys)
+    merged = merge_top_keys(parts, top)
+    _check_keys(oracle, want, merged, top)
+
+
+def test_reference_signature_entry_on_all_gpus(oracle):
+    """swimm_gpu_search_avx2_compat with n_threads = number of GPUs (0 = all visible): the database is sharded over them
+    and every GPU fills its own entries of the reference-layout score array."""
+    from swimm_b200 import gpu as g
+    db, dl, dc, do = _db(41, 1000, hi=500)
+    ql, qc, qo = _queries(42, [30, 144, 1100], db)
+    _, dl, dc = synth.length_sorted(db)
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    vdb, vlen, vblocks, vdisp = synth.interleave_reference(dl, dc)
+    for n_threads in sorted({0, 1, g.device_count()}):
+        scores, _ = g.compat_search_avx2(qc, ql, qo, vdb, vlen, vblocks, vdisp, host.submat("blosum62"), 10, 2,
+                                         n_threads=n_threads)
+        assert np.array_equal(scores[:, :db.n], want), n_threads
+        assert (scores[:, db.n:] == 0).all()
