@@ -4,18 +4,22 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2] [--scale S]
 
 A step = one pass of the hot path over one batch: all queries of the workload against the resident
-database shard (query profiles, 16-bit kernels, 32-bit recomputation, top-r).  N=1 workload: BASELINE.json
+database shard (query profiles, 16-bit kernels, 32-bit recomputation, top-r).  Headline workload: BASELINE.json
 configs[1] ("cfg2": 20 queries of 144..5478 residues vs a synthetic Swiss-Prot-sized database, ~570k
-sequences / ~205M residues).  N>1: one process per GPU (torchrun), every rank holds one shard of an
-N-times larger database (weak scaling), no data-path collective; the per-rank hit lists are gathered
+sequences / ~205M residues per GPU).  N>1: one process per GPU (torchrun); ALL ranks build the same seeded
+database of N x 570k sequences and keep their own shard (tile round-robin), so per-GPU work is fixed (weak
+scaling) and the merged hit list can be verified; no data-path collective, the per-rank hit lists are gathered
 and merged once per step.
 
 value  = cells of all ranks / max-over-ranks device time (CUDA events on the library's stream),
          inputs resident in HBM.
 e2e    = the same through swg_gpu_search() with host buffers: query H2D + kernels + top-r + hit-list D2H
          (+ the cross-rank gather/merge) inside the timed region, wall clock, max over ranks.
+strong = measured in the same run after the headline: fixed databases (cfg3 = 6M sequences / 1.3G residues, cfg1 =
+         100k sequences) split over the N ranks; GCUPS of the whole job.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -42,6 +46,10 @@ from swimm_b200 import host, synth  # noqa: E402
 
 METRIC = "GCUPS (whole box) Swiss-Prot-scale synthetic search"
 GO, GE, MATRIX, TOP = 10, 2, "blosum62", 10
+# one sampling rule for both CPU legs (cpu_baseline of our arm, and --impl reference): every k-th sequence of the
+# shard, k chosen so that the sample is about this many cells per step (all queries)
+CPU_SAMPLE_CELLS = 6e11
+NCU_JSON = "profiles/r02_ncu_full_cfg2_kernels.json"
 
 
 def log(*a):
@@ -92,30 +100,55 @@ def physical_device_index(local_rank):
 
 
 # ---------------------------------------------------------------------------------------------------
-def make_shard(workload, scale, rank, world):
-    """This rank's shard of the (world x larger) database + the queries, in the library's input form."""
-    t0 = time.time()
-    if workload == "cfg2":
-        q = synth.make_queries(np.random.default_rng(7), synth.QUERY_LENGTHS)
-        n_local = max(64, int(570_000 * scale)) // 16 * 16
-        db = synth.make_db(1000 + rank, n_local, mu=5.675, queries=q)
-    elif workload == "cfg1":
-        q = synth.make_queries(np.random.default_rng(42), [144])
-        n_local = max(64, int(100_000 * scale)) // 16 * 16
-        db = synth.make_db(42 + rank, n_local, queries=q)
-    elif workload == "cfg3":      # Environmental-NR-sized TOTAL, split over the ranks
-        q = synth.make_queries(np.random.default_rng(7), synth.QUERY_LENGTHS)
-        n_local = max(64, int(6_000_000 * scale / world)) // 16 * 16
-        db = synth.make_db(3000 + rank, n_local, mu=5.2, sigma=0.6, queries=q)
-    else:
-        raise SystemExit("unknown workload %s" % workload)
-    _, dl, dc = synth.length_sorted(db)
-    _, ql, qc = synth.length_sorted(q)
-    qo = np.zeros(q.n + 1, np.uint32)
-    np.cumsum(ql.astype(np.uint32), out=qo[1:])
-    log("[rank %d] shard: %d sequences, %d residues, %d queries (%.1f s to generate)"
-        % (rank, len(dl), len(dc), q.n, time.time() - t0))
-    return q, ql, qc, qo, dl, dc
+class Workload:
+    """Queries + the WHOLE length-sorted database of a BASELINE.json configuration (every rank builds the same one)."""
+
+    def __init__(self, name, scale=1.0, world=1, weak=False):
+        t0 = time.time()
+        self.name = name
+        mult = world if weak else 1
+        if name == "cfg2":      # Swiss-Prot-sized, 20 queries; weak scaling: `world` times as many sequences
+            self.q = synth.make_queries(np.random.default_rng(7), synth.QUERY_LENGTHS)
+            n = max(64, int(570_000 * scale)) // 16 * 16 * mult
+            self.dl, self.dc = synth.sorted_db(1000, n, mu=5.675, queries=self.q)
+        elif name == "cfg1":    # one 144-residue query vs 100k sequences
+            self.q = synth.make_queries(np.random.default_rng(42), [144])
+            n = max(64, int(100_000 * scale)) // 16 * 16 * mult
+            self.dl, self.dc = synth.sorted_db(42, n, queries=self.q)
+        elif name == "cfg3":    # Environmental-NR-sized
+            self.q = synth.make_queries(np.random.default_rng(7), synth.QUERY_LENGTHS)
+            n = max(64, int(6_000_000 * scale)) // 16 * 16 * mult
+            self.dl, self.dc = synth.sorted_db(3000, n, mu=5.2, sigma=0.6, queries=self.q)
+        elif name == "cfg4":    # long-sequence stress: every sequence longer than 3000 residues, up to the format's 65535
+            rng = np.random.default_rng(44)
+            self.q = synth.make_queries(rng, [144, 1000, 3100, 5478])
+            n = max(64, int(8000 * scale)) // 16 * 16
+            lens = np.concatenate([rng.integers(3001, 20000, n - 8), [30000, 40000, 50000, 60000, 65535, 65535, 3001, 3002]])
+            db = synth.make_seqset(rng, lens)
+            synth.plant(rng, db, self.q, fraction=0.02, frag_range=(50, 3000), rate=0.1)
+            _, self.dl, self.dc = synth.length_sorted(db)
+        elif name == "cfg5":    # multi-query batch for the matrix / penalty sweep, on the cfg1 database
+            self.q = synth.make_queries(np.random.default_rng(55), [61, 144, 222, 375, 567, 850, 1321, 2005])
+            n = max(64, int(100_000 * scale)) // 16 * 16
+            self.dl, self.dc = synth.sorted_db(42, n, queries=self.q, plant_fraction=0.005)
+        else:
+            raise SystemExit("unknown workload %s" % name)
+        _, self.ql, self.qc = synth.length_sorted(self.q)
+        self.qo = np.zeros(self.q.n + 1, np.uint32)
+        np.cumsum(self.ql.astype(np.uint32), out=self.qo[1:])
+        self.q_res = int(self.ql.astype(np.int64).sum())
+        self.n_total = len(self.dl)
+        self.residues = len(self.dc)
+        self.cells = self.q_res * self.residues
+        self.gen_s = time.time() - t0
+
+    def shard(self, rank, world):
+        return synth.shard_of(self.dl, self.dc, rank, world)
+
+    def describe(self, world=1):
+        return "%s: %d queries (%d..%d residues, %d total) x %d sequences / %d residues%s" % (
+            self.name, self.q.n, int(self.ql.min()), int(self.ql.max()), self.q_res, self.n_total // world,
+            self.residues // world, " per GPU" if world > 1 else "")
 
 
 def reference_binary():
@@ -123,7 +156,7 @@ def reference_binary():
     return p if os.path.exists(p) and os.access(p, os.X_OK) else None
 
 
-def run_reference_once(q, dl, dc, threads, tmp, queries_subset=None):
+def run_reference_once(q, dl, dc, threads, tmp):
     """Time the unmodified reference (oracle/_ref/swimm -S search -m 0 -v 32) on preprocessed files written
     in its own format; returns (search_seconds_printed, cells)."""
     prefix = os.path.join(tmp, "db")
@@ -137,30 +170,25 @@ def run_reference_once(q, dl, dc, threads, tmp, queries_subset=None):
         with open(prefix + ".desc", "w") as f:
             for i in range(n):
                 f.write(">syn|%09d| s\n" % i)
-    idx = list(range(q.n)) if queries_subset is None else queries_subset
-    qf = os.path.join(tmp, "q_%s.fasta" % "_".join(map(str, idx)))
+    qf = os.path.join(tmp, "q.fasta")
     if not os.path.exists(qf):
-        sub = synth.SeqSet(np.concatenate([q.seq(i) for i in idx]),
-                           np.concatenate([[0], np.cumsum([len(q.seq(i)) for i in idx])]).astype(np.int64),
-                           [q.title(i) for i in idx])
-        synth.write_fasta(qf, sub)
+        synth.write_fasta(qf, q)
     out = subprocess.run([reference_binary(), "-S", "search", "-q", qf, "-d", prefix, "-m", "0", "-v", "32", "-c",
                           str(threads), "-r", str(TOP)], capture_output=True, text=True, check=True).stdout
     secs = None
     for line in out.splitlines():
         if line.startswith("Search time:"):
             secs = float(line.split()[2])
-    cells = int(sum(len(q.seq(i)) for i in idx)) * int(len(dc))
+    cells = int(sum(len(q.seq(i)) for i in range(q.n))) * int(len(dc))
     return secs, cells
 
 
-def cpu_baseline_sample(q, dl, dc, target_cells=1.5e12):
-    """A bounded sample of the workload for the CPU legs: the first sequences of the shard (every 8th tile keeps
-    the length mix) and all queries, sized to ~10-30 s of reference time."""
+def cpu_sample(q, dl, dc):
+    """The bounded sample of the workload both CPU legs time: every k-th sequence of the (length-sorted) shard, which
+    keeps the length mix, and all queries; k from CPU_SAMPLE_CELLS."""
     n = len(dl)
-    want_res = target_cells / float(sum(len(q.seq(i)) for i in range(q.n)))
-    frac = min(1.0, want_res / max(1, len(dc)))
-    stride = max(1, int(round(1.0 / frac)))
+    want_res = CPU_SAMPLE_CELLS / float(sum(len(q.seq(i)) for i in range(q.n)))
+    stride = max(1, int(round(max(1, len(dc)) / want_res)))
     off = np.zeros(n + 1, np.int64)
     np.cumsum(dl.astype(np.int64), out=off[1:])
     keep = np.arange(0, n, stride)
@@ -169,6 +197,17 @@ def cpu_baseline_sample(q, dl, dc, target_cells=1.5e12):
         np.arange(int(sl.astype(np.int64).sum()))
     return sl, dc[idx], "every %d-th sequence of the shard (%d sequences, %d residues) x all %d queries" % (
         stride, len(sl), len(idx), q.n)
+
+
+def full_size_crosscheck():
+    """The reference CLI timed on the FULL cfg2 workload on a GPU box (tools/full_parity.py, committed transcript)."""
+    for name in ("r02_cfg2_full_size_parity_vs_reference_cli.txt", "r01_cfg2_full_size_parity_vs_reference_cli.txt"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            for line in open(p):
+                if line.startswith("reference:"):
+                    return {"source": "profiles/" + name, "line": line.strip()}
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -182,6 +221,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipebench", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling legs and the other BASELINE configs")
+    ap.add_argument("--strong-scale", type=float, default=1.0, help="size of the fixed cfg3 database of the strong-scaling leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -202,24 +243,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    q, ql, qc, qo, dl, dc = make_shard(args.workload, args.scale, rank, world)
-    n_local = len(dl)
-    n_total = n_local * world
-    b62 = host.submat(MATRIX)
-    q_res = int(ql.astype(np.int64).sum())
-    cells_local = q_res * int(len(dc))
-
-    s = gpu.GpuSearch(local_rank)
-    t0 = time.time()
-    s.load_db_shard(dl, dc, rank, world, n_total)
-    db_load_s = time.time() - t0
-    st0 = s.stats()
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        s.sync()
 
     def max_over_ranks(x):
         if world == 1:
@@ -228,18 +255,33 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    b62 = host.submat(MATRIX)
+    wl = Workload(args.workload, args.scale, world, weak=True)
+    dl, dc, gidx = wl.shard(rank, world)
+    log("[rank %d] %s; this shard: %d sequences, %d residues (%.1f s to generate)"
+        % (rank, wl.describe(world), len(dl), len(dc), wl.gen_s))
+    q, ql, qc, qo = wl.q, wl.ql, wl.qc, wl.qo
+    cells_local = wl.q_res * int(len(dc))
+    cells_all = float(wl.cells)
+
+    s = gpu.GpuSearch(local_rank)
+    t0 = time.time()
+    s.load_db_shard(dl, dc, rank, world, wl.n_total)
+    db_load_s = time.time() - t0
+    st0 = s.stats()
 
     # pinned host buffers for the end-to-end leg
     pin_q = torch.from_numpy(qc.copy()).pin_memory()
     pin_keys = torch.zeros((q.n, TOP), dtype=torch.int64).pin_memory()
     keys_np = pin_keys.numpy().view(np.uint64)
     gather = [torch.zeros((q.n, TOP), dtype=torch.int64, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def merge(keys):
+        if world == 1:
+            return keys
+        # the one exchange step of the path: r keys per query per GPU, merged on every rank
+        dist.all_gather(gather, torch.from_numpy(keys.view(np.int64)).cuda(non_blocking=True))
+        return gpu.merge_top_keys([g.cpu().numpy().view(np.uint64) for g in gather], TOP)
 
     def step_resident():
         s.run(TOP)
@@ -249,12 +291,7 @@ def main():
         s.set_queries(pin_q.numpy(), ql, qo[:-1], b62, GO, GE)
         s.run(TOP)
         s.fetch(False, True, keys_out=keys_np)
-        if world > 1:      # the one exchange step of the path: r keys per query per GPU, merged on every rank
-            dist.all_gather(gather, pin_keys.cuda(non_blocking=True))
-            merged = gpu.merge_top_keys([g.cpu().numpy().view(np.uint64) for g in gather], TOP)
-        else:
-            merged = keys_np
-        return merged
+        return merge(keys_np)
 
     # ---- value: inputs resident ----
     s.set_queries(qc, ql, qo[:-1], b62, GO, GE)
@@ -262,6 +299,7 @@ def main():
         step_resident()
     sampler = ClockSampler(physical_device_index(local_rank))
     barrier()
+    s.sync()
     sampler.start()
     dev_s, search_s, topr_s, launches = 0.0, 0.0, 0.0, 0
     q_secs = np.zeros(q.n)
@@ -280,9 +318,7 @@ def main():
     sampler.join(timeout=2)
     dev_max = max_over_ranks(dev_s)
     wall_max = max_over_ranks(wall_s)
-    cells_all = sum_over_ranks(cells_local)
     value = cells_all * args.steps / dev_max / 1e9
-    rescored = s.stats()["rescored"]
 
     # ---- e2e: host buffers in, hit lists out ----
     for _ in range(max(1, args.warmup // 2)):
@@ -293,112 +329,257 @@ def main():
         merged = step_e2e()
     barrier()
     e2e_s = max_over_ranks(time.time() - e0)
+    merged = np.array(merged, copy=True)          # (one rank: the pinned buffer itself, reused below)
     st = s.stats()
+    rescored = st["rescored"]             # filled by fetch (the resident loop does not download the counters)
     e2e = {"value": cells_all * args.steps / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(st["h2d_bytes"]),
            "d2h_bytes_per_step": int(st["d2h_bytes"]), "ms_per_step": e2e_s / args.steps * 1e3}
 
+    # ---- e2e, streaming: back-to-back batches through submit/poll (batch k+1 is uploaded and queued while k computes) ----
+    nb = max(4, args.steps + 1)
+    barrier()
+    s0_ = time.time()
+    tickets = [s.submit(pin_q.numpy(), ql, qo[:-1], b62, GO, GE, TOP)]
+    for b in range(1, nb):
+        tickets.append(s.submit(pin_q.numpy(), ql, qo[:-1], b62, GO, GE, TOP))
+        k_, _ = s.poll(tickets[b - 1], True, keys_out=keys_np)
+        merged_stream = merge(keys_np)
+    s.poll(tickets[-1], True, keys_out=keys_np)
+    merged_stream = merge(keys_np)
+    barrier()
+    stream_s = max_over_ranks(time.time() - s0_)
+    e2e_stream = {"value": cells_all * nb / stream_s / 1e9, "unit": "GCUPS", "batches": nb,
+                  "ms_per_batch": stream_s / nb * 1e3, "same_hits_as_blocking_call": bool(np.array_equal(merged_stream, merged))}
+
+    # ---- merged hit list: verified on rank 0 against a single-GPU search of a sampled subset of the ONE database ----
+    merged_ok, merged_note = None, None
+    if rank == 0:
+        ks, ki = gpu.split_key(merged)
+        hits = np.unique(ki.ravel())
+        stride = max(1, wl.n_total // 20000)
+        sub = np.unique(np.concatenate([hits, np.arange(0, wl.n_total, stride)]))
+        off = np.zeros(wl.n_total + 1, np.int64)
+        np.cumsum(wl.dl.astype(np.int64), out=off[1:])
+        sl = wl.dl[sub]
+        idx = np.repeat(off[sub] - np.concatenate([[0], np.cumsum(sl.astype(np.int64))[:-1]]), sl.astype(np.int64)) + \
+            np.arange(int(sl.astype(np.int64).sum()))
+        chk = gpu.GpuSearch(local_rank)
+        chk.load_db(sl, wl.dc[idx])
+        sc, _ = chk.search(qc, ql, qo[:-1], b62, GO, GE, 0, want_scores=True)
+        chk.close()
+        # (1) every merged hit has exactly the score the single-GPU search gives that sequence; (2) no sampled sequence
+        # that is missing from a query's list beats the list's last hit (key order: score, then index)
+        pos = {int(g): i for i, g in enumerate(sub)}
+        ok = True
+        for qi in range(q.n):
+            cols = np.array([pos[int(g)] for g in ki[qi]])
+            ok = ok and bool(np.array_equal(sc[qi, cols], ks[qi]))
+            keys_sub = (sc[qi].astype(np.uint64) << np.uint64(32)) | sub.astype(np.uint64)
+            last = np.uint64(merged[qi, -1])
+            better = sub[keys_sub > last]
+            ok = ok and bool(np.isin(better, ki[qi]).all())
+            ok = ok and bool((np.diff(merged[qi].astype(np.int64)) < 0).all())
+        merged_ok = ok
+        digest = hashlib.sha256(np.ascontiguousarray(merged).tobytes()).hexdigest()[:16]
+        merged_note = ("merged top-%d of all %d ranks (ONE database of %d sequences, tile round-robin shards) checked on rank 0 "
+                       "against an unsharded single-GPU search of %d sampled sequences + all hit sequences: hit scores equal, "
+                       "no sampled non-hit beats a list's last key, keys strictly descending; sha256[:16] of the merged keys %s"
+                       % (TOP, world, wl.n_total, len(sub) - len(hits), digest))
+
+    # ---- roofline: the integer/SIMD pipe for each kernel's own instruction mix, measured live ----
+    roof, peaks = None, None
+    if rank == 0 and not args.no_pipebench:
+        roof = roofline(s, gpu, q_secs, ql, len(dc), args.steps, st, search_s, cells_local, dev_s)
+        peaks = roof.pop("_peaks")
+
+    # ---- strong scaling + the other BASELINE configurations, measured in the same run ----
+    strong, configs = None, None
+    if not args.no_extra:
+        strong = {}
+        for name, sc_, steps_, warm_ in (("cfg3", args.strong_scale, 2, 1), ("cfg1", 1.0, 20, 5)):
+            w2 = Workload(name, sc_, world, weak=False)
+            l2, c2, _ = w2.shard(rank, world)
+            s.load_db_shard(l2, c2, rank, world, w2.n_total)
+            s.set_queries(w2.qc, w2.ql, w2.qo[:-1], b62, GO, GE)
+            for _ in range(warm_):
+                step_resident()
+            barrier()
+            s.sync()
+            d2 = 0.0
+            for _ in range(steps_):
+                step_resident()
+                d2 += s.stats()["device_seconds"]
+            barrier()
+            d2 = max_over_ranks(d2)
+            strong[name] = {"workload": w2.describe(), "n_gpus": world, "steps": steps_, "warmup": warm_,
+                            "ms_per_step": d2 / steps_ * 1e3, "gcups": w2.cells * steps_ / d2 / 1e9,
+                            "note": "fixed total database split over the ranks by tiles; efficiency = gcups / (N x the N=1 line's gcups)"}
+            log("[rank %d] strong %s: %.3f ms/step" % (rank, name, d2 / steps_ * 1e3))
+            del w2, l2, c2
+        if world == 1:
+            configs = other_configs(s, gpu, peaks)
+    s.close()
+
     if rank != 0:
-        s.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline: the integer/SIMD pipe for each kernel's own instruction mix, measured live ----
-    roof = None
-    if not args.no_pipebench:
-        pb = s.pipebench()
-        fast = (GO + GE, GE) == (12, 2)         # default penalties run the kernels whose penalties are immediates
-        kinds = s.query_kernels()
-        kernels = {}
-        # sequence-pair kernel: 6.5 integer instructions per 2 cells; query-pair kernel: 5.5 (no score-pack PRMT).
-        # peak cells/s = dependency-free issue rate of that mix * 2 / instructions per cell pair
-        for kind, name, probe, ipc2, mix_text in [
-                (0, "wavefront_kernel<Lane16,G,K> (one query x two database sequences per register)",
-                 "mix_v2_immediate_penalties" if fast else "mix_v2_4p5_alu_2_viadd", 6.5,
-                 "6.5 integer instr per 2 cells: 4.5 on the ALU pipe (PRMT, VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + 2 VIADD.16x2"),
-                (1, "wavefront_q2_kernel<G,K> (two queries x one database sequence per register)",
-                 "mix_q2_3p5alu_2viadd_immediate" if fast else "mix_c_hef_best_3p5alu_2viadd", 5.5,
-                 "5.5 integer instr per 2 cells: 3.5 on the ALU pipe (VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + 2 VIADD.16x2")]:
-            sel = kinds == kind
-            secs = float(q_secs[sel].sum())
-            if secs <= 0:
-                continue
-            mix = pb["probes"][probe]
-            cells_k = float(ql[sel].astype(np.int64).sum()) * len(dc) * args.steps
-            peak = mix["ginstr_per_s"] * 2.0 / ipc2
-            kernels[kind] = {"kernel": name, "queries": int(sel.sum()), "share_of_search_time": secs / float(q_secs.sum()),
-                             "achieved": cells_k / secs / 1e9, "peak": peak, "frac": cells_k / secs / 1e9 / peak,
-                             "mix": mix_text + "; measured %.1f thread-instr/clk/SM at %.0f MHz"
-                                    % (mix["thread_instr_per_clk_per_sm"], mix["sm_mhz"])}
-        dom = max(kernels.values(), key=lambda k: k["share_of_search_time"])
-        others = [k for k in kernels.values() if k is not dom]
-        per_gpu = cells_local * args.steps / dev_s / 1e9
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] \
-            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        # algorithmic HBM bytes: the tiled database once per search launch + the pass lines of the query-pair kernel
-        algo_gbs = st["stream_bytes"] * args.steps / search_s / 1e9
-        # DRAM traffic of the dominant kernel's launches from the committed ncu --set full captures (read + written)
-        traffic, traffic_note = None, None
-        try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_cfg2_kernels.json")))
-            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            key = "q2_middle_pass" if dom is kernels.get(1) else "seqpair_q144"
-            traffic = sum(float(cap[key][k].split()[0]) * unit[cap[key][k].split()[1]]
-                          for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-            algo_launch = st["stream_bytes"] / max(1, st["pair_launches"]) if dom is kernels.get(1) else st["db_bytes"]
-            traffic_note = ("ncu dram bytes read+written by one full-size launch (profiles/r01_ncu_full_cfg2_kernels.json, %s); "
-                            "algorithmic bytes: the tiled database (%d) once per launch, plus -- query-pair kernel, launches that "
-                            "continue a query -- the pass lines, 8 B per database column read and 8 B written; average over "
-                            "this run's launches %.0f" % (key, st["db_bytes"], algo_launch))
-        except Exception:
-            pass
-        roof = {"bound": "int_alu", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "GCUPS",
-                "frac": dom["frac"], "traffic": traffic, "traffic_note": traffic_note,
-                "kernel": dom["kernel"], "mix": dom["mix"], "share_of_search_time": dom["share_of_search_time"],
-                "other_kernels": others, "whole_step_gcups_per_gpu": per_gpu,
-                "hbm": {"bound": "hbm", "achieved": algo_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": algo_gbs / hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json"))
-                        else "fallback"},
-                "pipebench": {k: round(v["thread_instr_per_clk_per_sm"], 2) for k, v in pb["probes"].items()}}
-    s.close()
-
     cpu_base = None
     if not args.no_cpu_baseline and reference_binary():
-        sl, sc, what = cpu_baseline_sample(q, dl, dc)
+        sl, sc, what = cpu_sample(q, dl, dc)
         with tempfile.TemporaryDirectory() as tmp:
             run_reference_once(q, sl, sc, cores, tmp)                 # warm-up (page cache, OpenMP pool)
-            secs, cells = run_reference_once(q, sl, sc, cores, tmp)
-        cpu_base = {"value": cells / secs / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
-                    "sample": what + "; swimm -S search -m 0 -v 32 -c %d, printed Search time %.3f s" % (cores, secs)}
+            t_cpu, runs = [], 0
+            t_begin = time.time()
+            while runs < 3 or (time.time() - t_begin < 12 and runs < 12):
+                secs, cells = run_reference_once(q, sl, sc, cores, tmp)
+                t_cpu.append(secs)
+                runs += 1
+        med = float(np.median(t_cpu))
+        cpu_base = {"value": cells / med / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                    "sample": what + "; swimm -S search -m 0 -v 32 -c %d, median printed Search time of %d runs %.3f s "
+                                     "(the same sample --impl reference times)" % (cores, runs, med),
+                    "full_size_crosscheck": full_size_crosscheck()}
 
     line = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_max / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "s16x2 (exact int32 result)", "data": "synthetic",
-            "config": {"workload": "%s: %d queries (%d..%d residues, %d total) x %d sequences / %d residues per GPU, "
-                                   "BLOSUM62, gap 10/2, top %d" % (args.workload, q.n, int(ql.min()), int(ql.max()), q_res,
-                                                                    n_local, len(dc), TOP),
-                       "sharding": "tile round-robin, one shard per GPU, hit lists merged per step",
+            "config": {"workload": wl.describe(world) + ", BLOSUM62, gap 10/2, top %d" % TOP,
+                       "sharding": "ONE seeded database of %d sequences; tile round-robin, one shard per GPU, hit lists "
+                                   "merged per step" % wl.n_total,
                        "l2": "tiled database per GPU (%d MB) exceeds the 126 MB L2; every search launch streams it once"
-                             % (st["db_bytes"] >> 20)},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
-            "roofline": roof, "cpu_baseline": cpu_base,
+                             % (st0["db_bytes"] >> 20)},
+            "e2e": e2e, "e2e_stream": e2e_stream, "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "merged_ok": merged_ok, "merged_note": merged_note,
+            "roofline": roof, "cpu_baseline": cpu_base, "strong": strong,
             "detail": {"search_ms_per_step": search_s / args.steps * 1e3, "topr_ms_per_step": topr_s / args.steps * 1e3,
                        "wall_ms_per_step": wall_max / args.steps * 1e3, "db_load_seconds": db_load_s,
                        "rescored_lanes": int(rescored), "db_bytes": int(st0["db_bytes"]),
                        "per_query_gcups": {str(int(ql[i])): round(float(ql[i]) * len(dc) * args.steps / q_secs[i] / 1e9, 1)
-                                           for i in range(q.n) if q_secs[i] > 0}}}
+                                           for i in range(q.n) if q_secs[i] > 0},
+                       "configs": configs}}
     if world > 1:
         dist.destroy_process_group()
     emit(line)
     return 0
 
 
+KERNELS = [
+    # kind, name, pipebench probe (default penalties as immediates / generic), instr per 2 cells, ALU-pipe instr per 2 cells
+    (0, "wavefront_kernel<Lane16,G,K> (one query x two database sequences per register)",
+     ("mix_v2_immediate_penalties", "mix_v2_4p5_alu_2_viadd"), 6.5, 4.5,
+     "6.5 integer instr per 2 cells: 4.5 on the ALU pipe (PRMT, VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + 2 VIADD.16x2"),
+    (1, "wavefront_q2_kernel<G,K> (two queries x one database sequence per register)",
+     ("mix_q2_3p5alu_2viadd_immediate", "mix_c_hef_best_3p5alu_2viadd"), 5.5, 3.5,
+     "5.5 integer instr per 2 cells: 3.5 on the ALU pipe (VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + 2 VIADD.16x2"),
+]
+
+
+def kernel_peaks(pb, fast):
+    """Per kernel: peak GCUPS of its own measured dependency-free mix, and the strict ALU-pipe bound (64 lanes/clk/SM)."""
+    out = {}
+    for kind, name, probes, ipc2, alu2, mix_text in KERNELS:
+        mix = pb["probes"][probes[0] if fast else probes[1]]
+        strict = pb["sms"] * mix["sm_mhz"] * 1e6 * 64.0 * 2.0 / alu2 / 1e9
+        out[kind] = {"name": name, "peak": mix["ginstr_per_s"] * 2.0 / ipc2, "peak_strict": strict,
+                     "mix": mix_text + "; measured %.1f thread-instr/clk/SM at %.0f MHz"
+                            % (mix["thread_instr_per_clk_per_sm"], mix["sm_mhz"])}
+    return out
+
+
+def roofline(s, gpu, q_secs, ql, residues, steps, st, search_s, cells_local, dev_s):
+    pb = s.pipebench()
+    peaks = kernel_peaks(pb, (GO + GE, GE) == (12, 2))
+    kinds = s.query_kernels()
+    kernels = {}
+    for kind, pk in peaks.items():
+        sel = kinds == kind
+        secs = float(q_secs[sel].sum())
+        if secs <= 0:
+            continue
+        cells_k = float(ql[sel].astype(np.int64).sum()) * residues * steps
+        kernels[kind] = {"kernel": pk["name"], "queries": int(sel.sum()), "share_of_search_time": secs / float(q_secs.sum()),
+                         "achieved": cells_k / secs / 1e9, "peak": pk["peak"], "frac": cells_k / secs / 1e9 / pk["peak"],
+                         "peak_strict_alu_pipe": pk["peak_strict"], "frac_strict_alu_pipe": cells_k / secs / 1e9 / pk["peak_strict"],
+                         "mix": pk["mix"]}
+    dom = max(kernels.values(), key=lambda k: k["share_of_search_time"])
+    others = [k for k in kernels.values() if k is not dom]
+    per_gpu = cells_local * steps / dev_s / 1e9
+    have_peaks = os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json"))
+    hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if have_peaks else 6650.0
+    # algorithmic HBM bytes: the tiled database once per search launch + the pass lines of the query-pair kernel
+    algo_gbs = st["stream_bytes"] * steps / search_s / 1e9
+    # DRAM traffic of the dominant kernel's launches from the committed ncu --set full captures (read + written)
+    traffic, traffic_note = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, NCU_JSON)))
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        key = "q2_middle_pass" if dom is kernels.get(1) else "seqpair_q144"
+        traffic = sum(float(cap[key][k].split()[0]) * unit[cap[key][k].split()[1]]
+                      for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        traffic_note = ("ncu dram bytes read+written by one full-size launch of the dominant kernel (%s, %s); algorithmic bytes of "
+                        "such a launch: the tiled database (%d) + -- query-pair kernel, launches that continue a query -- the "
+                        "pass lines, 8 B per database column read and 8 B written" % (NCU_JSON, key, st["db_bytes"]))
+    except Exception:
+        pass
+    return {"bound": "int_alu", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "GCUPS",
+            "frac": dom["frac"], "peak_strict_alu_pipe": dom["peak_strict_alu_pipe"],
+            "frac_strict_alu_pipe": dom["frac_strict_alu_pipe"], "traffic": traffic, "traffic_note": traffic_note,
+            "kernel": dom["kernel"], "mix": dom["mix"], "share_of_search_time": dom["share_of_search_time"],
+            "other_kernels": others, "whole_step_gcups_per_gpu": per_gpu,
+            "hbm": {"bound": "hbm", "achieved": algo_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": algo_gbs / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if have_peaks else "fallback"},
+            "pipebench": {k: round(v["thread_instr_per_clk_per_sm"], 2) for k, v in pb["probes"].items()},
+            "_peaks": peaks}
+
+
+def other_configs(s, gpu, peaks):
+    """BASELINE.json configs[0], [3], [4] on this GPU, after the headline: GCUPS of the whole batch, which kernel took most
+    of the time and the fraction of that kernel's roofline."""
+    out = {}
+    generic_peaks = None
+    runs = [("cfg1", "blosum62", 10, 2, 20, 5), ("cfg4", "blosum62", 10, 2, 3, 2),
+            ("cfg5", "blosum45", 8, 2, 10, 3), ("cfg5", "pam250", 12, 1, 10, 3)]
+    loaded = None
+    for name, matrix, go, ge, steps, warm in runs:
+        if loaded is None or loaded.name != name:
+            loaded = Workload(name)
+            s.load_db(loaded.dl, loaded.dc)
+        w = loaded
+        s.set_queries(w.qc, w.ql, w.qo[:-1], host.submat(matrix), go, ge)
+        for _ in range(warm):
+            s.run(TOP)
+            s.sync()
+        dev, qs = 0.0, np.zeros(w.q.n)
+        for _ in range(steps):
+            s.run(TOP)
+            s.sync()
+            dev += s.stats()["device_seconds"]
+            qs += s.query_seconds()
+        kinds = s.query_kernels()
+        share1 = float(qs[kinds == 1].sum()) / max(float(qs.sum()), 1e-12)
+        kind = 1 if share1 >= 0.5 else 0
+        gc = w.cells * steps / dev / 1e9
+        rec = {"workload": w.describe() + ", %s, gap %d/%d" % (matrix, go, ge), "gcups": gc, "ms_per_step": dev / steps * 1e3,
+               "dominant_kernel": KERNELS[kind][1], "share_of_search_time": share1 if kind else 1.0 - share1}
+        if peaks:
+            fast = (go + ge, ge) == (12, 2)
+            if not fast and generic_peaks is None:
+                generic_peaks = kernel_peaks(s.pipebench(), False)
+            pk = peaks[kind] if fast else generic_peaks[kind]
+            rec.update({"peak": pk["peak"], "frac": gc / pk["peak"], "frac_strict_alu_pipe": gc / pk["peak_strict"]})
+        out["%s %s %d/%d" % (name, matrix, go, ge)] = rec
+        log("[config] %s %s %d/%d: %.0f GCUPS" % (name, matrix, go, ge, gc))
+    return out
+
+
 def bench_reference(args, cores):
     """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
-    q, ql, qc, qo, dl, dc = make_shard(args.workload, args.scale, 0, 1)
-    q_res = int(ql.astype(np.int64).sum())
+    wl = Workload(args.workload, args.scale, 1)
+    q, ql, qc, qo, dl, dc = wl.q, wl.ql, wl.qc, wl.qo, wl.dl, wl.dc
     kind = "reference" if reference_binary() else "port"
-    sl, sc, what = cpu_baseline_sample(q, dl, dc, target_cells=6e11)
+    sl, sc, what = cpu_sample(q, dl, dc)
     times = []
     with tempfile.TemporaryDirectory() as tmp:
         if kind == "reference":
@@ -411,7 +592,7 @@ def bench_reference(args, cores):
             oracle = load_oracle()
             so = np.zeros(len(sl) + 1, np.uint64)
             np.cumsum(sl.astype(np.uint64), out=so[1:])
-            cells = q_res * len(sc)
+            cells = wl.q_res * len(sc)
             for i in range(args.warmup + args.steps):
                 t0 = time.time()
                 oracle.search(qc, qo, sc, so, host.submat(MATRIX), GO, GE, threads=cores)
@@ -423,11 +604,12 @@ def bench_reference(args, cores):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s8/s16/s32 AVX2",
             "data": "synthetic",
-            "config": {"workload": "%s: %d queries (%d..%d residues, %d total), BLOSUM62, gap 10/2, top %d"
-                                   % (args.workload, q.n, int(ql.min()), int(ql.max()), q_res, TOP)},
+            "config": {"workload": wl.describe() + ", BLOSUM62, gap 10/2, top %d" % TOP},
             "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": cores, "kind": kind,
-                             "sample": what + ("; swimm -S search -m 0 -v 32 -c %d (printed Search time)" % cores
-                                               if kind == "reference" else "; scalar oracle port, OpenMP")},
+                             "sample": what + ("; swimm -S search -m 0 -v 32 -c %d (printed Search time); GCUPS is a rate: "
+                                               "the full-size run agrees, see full_size_crosscheck" % cores
+                                               if kind == "reference" else "; scalar oracle port, OpenMP"),
+                             "full_size_crosscheck": full_size_crosscheck()},
             "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0

@@ -72,6 +72,11 @@ const char *swg_gpu_last_error(const swg_ctx *ctx);           /* static string w
  * t % num_shards == shard, so every shard gets the same residue count and length mix. */
 int swg_gpu_load_db(swg_ctx *ctx, const uint16_t *lengths, const signed char *residues,
                     uint64_t n_sequences, uint64_t n_residues, int shard, int num_shards);
+/* same, when the caller already holds the prefix sums of the lengths (offsets[i] = first residue of sequence i,
+ * offsets[n_sequences] = n_residues; what the host keeps after reading <db>.seq): a shard then visits only its own
+ * tiles instead of walking the whole length array -- one host thread per GPU can load all shards at the same time. */
+int swg_gpu_load_db_offsets(swg_ctx *ctx, const uint16_t *lengths, const uint64_t *offsets, const signed char *residues,
+                            uint64_t n_sequences, uint64_t n_residues, int shard, int num_shards);
 /* same, when the caller holds only this shard's sequences (tiles shard, shard+num_shards, ... of the whole
  * length-sorted database, back to back): what one process per GPU loads in a multi-GPU job. */
 int swg_gpu_load_db_shard(swg_ctx *ctx, const uint16_t *local_lengths, const signed char *local_residues,

@@ -508,8 +508,8 @@ static int upload_and_build(swg_ctx *ctx, const std::vector<uint16_t> &len, cons
     return st;
 }
 
-int swg_gpu_load_db(swg_ctx *ctx, const uint16_t *lengths, const signed char *residues, uint64_t n_sequences,
-                    uint64_t n_residues, int shard, int num_shards)
+static int load_db_impl(swg_ctx *ctx, const uint16_t *lengths, const uint64_t *offsets, const signed char *residues,
+                        uint64_t n_sequences, uint64_t n_residues, int shard, int num_shards)
 {
     if (!ctx) return fail(nullptr, SWG_ERR_ARG, "ctx is NULL");
     if (num_shards < 1 || shard < 0 || shard >= num_shards) return fail(ctx, SWG_ERR_ARG, "shard %d of %d", shard, num_shards);
@@ -527,7 +527,18 @@ int swg_gpu_load_db(swg_ctx *ctx, const uint16_t *lengths, const signed char *re
     std::vector<uint16_t> len(ltiles * kTileSeqs, 0);
     std::vector<uint64_t> off(ltiles * kTileSeqs + 1, 0);
     std::vector<uint64_t> tile_src(ltiles + 1, 0);   // where each local tile's residues start in the caller's array
-    {
+    if (offsets) {
+        // the caller holds the prefix sums: only this shard's tiles are visited
+        if (offsets[n_sequences] != n_residues)
+            return fail(ctx, SWG_ERR_ARG, "offsets end at %llu residues, caller said %llu", (unsigned long long)offsets[n_sequences],
+                        (unsigned long long)n_residues);
+        for (uint64_t lt = 0; lt < ltiles; ++lt) {
+            const uint64_t g0 = (lt * num_shards + shard) * kTileSeqs;
+            tile_src[lt] = offsets[g0];
+            for (int k = 0; k < kTileSeqs; ++k)
+                if (g0 + k < n_sequences) len[lt * kTileSeqs + k] = lengths[g0 + k];
+        }
+    } else {
         uint64_t pos = 0, lt = 0;
         for (uint64_t t = 0; t < gtiles; ++t) {
             const bool mine = (t % num_shards) == (uint64_t)shard;
@@ -556,6 +567,19 @@ int swg_gpu_load_db(swg_ctx *ctx, const uint16_t *lengths, const signed char *re
     ctx->local_seqs = local_seqs;
     ctx->local_residues = local_res;
     return upload_and_build(ctx, len, off, residues, num_shards == 1 ? nullptr : tile_src.data());
+}
+
+int swg_gpu_load_db(swg_ctx *ctx, const uint16_t *lengths, const signed char *residues, uint64_t n_sequences,
+                    uint64_t n_residues, int shard, int num_shards)
+{
+    return load_db_impl(ctx, lengths, nullptr, residues, n_sequences, n_residues, shard, num_shards);
+}
+
+int swg_gpu_load_db_offsets(swg_ctx *ctx, const uint16_t *lengths, const uint64_t *offsets, const signed char *residues,
+                            uint64_t n_sequences, uint64_t n_residues, int shard, int num_shards)
+{
+    if (n_sequences && !offsets) return fail(ctx, SWG_ERR_ARG, "offsets is NULL");
+    return load_db_impl(ctx, lengths, offsets, residues, n_sequences, n_residues, shard, num_shards);
 }
 
 int swg_gpu_load_db_shard(swg_ctx *ctx, const uint16_t *local_lengths, const signed char *local_residues,
@@ -1324,9 +1348,8 @@ int swg_gpu_submit(swg_ctx *ctx, const signed char *queries, const uint16_t *q_l
     if (sl.busy) return fail(ctx, SWG_ERR_STATE, "two batches are in flight: poll ticket %d first", sl.ticket);
     SWG_CUDA(ctx, cudaSetDevice(ctx->device));
     swap_slot(ctx, sl);                  // the batch uses the slot's buffer set
-    int st = swg_gpu_set_queries(ctx, queries, q_lengths, q_disp, q_count, submat, open_gap, extend_gap);
-    cudaError_t e = cudaSuccess;
-    if (st == SWG_OK) e = cudaEventRecord(sl.ev_begin, ctx->stream);
+    cudaError_t e = cudaEventRecord(sl.ev_begin, ctx->stream);      // before the stream waits for the batch's upload
+    int st = e == cudaSuccess ? swg_gpu_set_queries(ctx, queries, q_lengths, q_disp, q_count, submat, open_gap, extend_gap) : SWG_OK;
     if (st == SWG_OK && e == cudaSuccess) st = swg_gpu_run(ctx, top, 0);
     const uint64_t n_keys = q_count * ctx->run_top;
     if (st == SWG_OK && e == cudaSuccess && n_keys > sl.h_keys_cap) {

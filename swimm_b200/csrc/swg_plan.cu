@@ -328,7 +328,7 @@ void plan_batch(const std::vector<uint16_t> &q_len, const ShardShape &shard, con
         if (opt.query_pairing && nq >= 2 && shard.ntiles) {
             // where the streams end and the single-pass pairs begin is a planner choice too
             double best = 1e300;
-            for (uint32_t above : {(uint32_t)kMaxPassRows, 832u, 640u, 448u, 256u}) {
+            for (uint32_t above : {(uint32_t)kMaxPassRows, 832u, 640u, 448u, 256u, 0u}) {
                 std::vector<WorkItem> cand;
                 const double c = build(above, cand);
                 if (c < best) { best = c; items.swap(cand); }

@@ -20,6 +20,7 @@ ABI_SYMBOLS = [
     "swg_gpu_set_queries", "swg_gpu_run", "swg_gpu_fetch", "swg_gpu_sync", "swg_gpu_get_stats", "swg_gpu_get_query_seconds",
     "swg_gpu_get_query_kernels", "swg_plan_describe", "swg_gpu_pipebench",
     "swg_gpu_set_option", "swg_gpu_debug_read", "swimm_gpu_search_avx2_compat", "swg_gpu_submit", "swg_gpu_poll",
+    "swg_gpu_load_db_offsets",
 ]
 
 
@@ -56,6 +57,7 @@ def load_library() -> C.CDLL:
     L.swg_gpu_last_error.argtypes = [vp]
     L.swg_gpu_last_error.restype = C.c_char_p
     L.swg_gpu_load_db.argtypes = [vp, vp, vp, u64, u64, i32, i32]
+    L.swg_gpu_load_db_offsets.argtypes = [vp, vp, vp, vp, u64, u64, i32, i32]
     L.swg_gpu_load_db_shard.argtypes = [vp, vp, vp, u64, u64, i32, i32, u64]
     L.swg_gpu_load_db_interleaved.argtypes = [vp, vp, vp, u64, vp, i32, u64, i32, i32]
     L.swg_gpu_db_local_sequences.argtypes = [vp]
@@ -148,10 +150,15 @@ class GpuSearch:
     def set_option(self, name: str, value: int):
         self._check(self.L.swg_gpu_set_option(self.ctx, name.encode(), int(value)), "set_option(%s)" % name)
 
-    def load_db(self, lengths, codes, shard: int = 0, num_shards: int = 1):
+    def load_db(self, lengths, codes, shard: int = 0, num_shards: int = 1, offsets=None):
         lengths = np.ascontiguousarray(lengths, dtype=np.uint16)
         codes = np.ascontiguousarray(codes, dtype=np.int8)
         self.n_total = len(lengths)
+        if offsets is not None:      # prefix sums of the lengths: the shard visits only its own tiles
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+            self._check(self.L.swg_gpu_load_db_offsets(self.ctx, lengths.ctypes.data, offsets.ctypes.data, codes.ctypes.data,
+                                                       len(lengths), len(codes), shard, num_shards), "load_db_offsets")
+            return
         self._check(self.L.swg_gpu_load_db(self.ctx, lengths.ctypes.data, codes.ctypes.data, len(lengths), len(codes),
                                            shard, num_shards), "load_db")
 

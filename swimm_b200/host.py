@@ -15,7 +15,7 @@ MATRICES = ["blosum45", "blosum50", "blosum62", "blosum80", "blosum90", "pam30",
 class SeqSetC(C.Structure):
     _fields_ = [("count", C.c_uint64), ("residues", C.c_uint64), ("lengths", C.POINTER(C.c_uint16)),
                 ("offsets", C.POINTER(C.c_uint64)), ("codes", C.POINTER(C.c_int8)),
-                ("titles", C.POINTER(C.c_char_p)), ("max_title", C.c_int)]
+                ("titles", C.POINTER(C.c_char_p)), ("max_title", C.c_int), ("input_pos", C.POINTER(C.c_uint64))]
 
 
 _lib = None

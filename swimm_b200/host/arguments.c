@@ -24,7 +24,9 @@ static struct argp_option options[] = {
     {"input", 'i', "<string>", 0, "Input sequence filename (must be in FASTA format). [REQUIRED]", 2},
     {"output", 'o', "<string>", 0, "Output filename. [REQUIRED]", 2},
     {0, 0, 0, 0, "search", 3},
-    {"query", 'q', "<string>", 0, "Input query sequence filename (must be in FASTA format). [REQUIRED]", 3},
+    {"query", 'q', "<string>", 0,
+     "Input query sequence filename (must be in FASTA format); several files separated by commas, or - to read file "
+     "names from standard input: the database stays resident and the files are searched as a stream of batches. [REQUIRED]", 3},
     {"db", 'd', "<string>", 0, "Preprocessed database output filename. [REQUIRED]", 3},
     {"sm", 's', "<string>", 0,
      "Substitution matrix. Supported values: blosum45, blosum50, blosum62, blosum80, blosum90, pam30, pam70, pam250 "
@@ -42,6 +44,11 @@ static struct argp_option options[] = {
     {"top", 'r', "<integer>", 0, "Number of scores to show (default: 10).", 3},
     {"max_chunk_size", 'k', "<integer>", 0, "Accepted for compatibility, ignored.", 3},
     {"block_size", 'b', "<integer>", 0, "Accepted for compatibility, ignored.", 3},
+    {"keep-input-order", 1001, 0, 0,
+     "Report the queries of a file in the order of the file.  Default: ascending length, the order the reference "
+     "reports (it sorts the queries, sequences.c:344; its own lengths array is copied before that sort, :276, so it "
+     "requires multi-query files that are already sorted -- this build accepts any order).", 3},
+    {"verbose", 1002, 0, 0, "Progress notes on stderr.", 3},
     {0}};
 
 typedef struct {
@@ -116,6 +123,8 @@ static int parse_opt(int key, char *arg, struct argp_state *state)
     }
     case 'k': o->max_chunk_size = strtoul(arg, NULL, 10); break;
     case 'b': o->block_size = atoi(arg); break;
+    case 1001: o->keep_input_order = 1; break;
+    case 1002: o->verbose = 1; break;
     case ARGP_KEY_END:
         if (ps->argc == 1)
             argp_failure(state, 1, 0, "Missing options");

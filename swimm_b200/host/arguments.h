@@ -28,6 +28,8 @@ typedef struct {
     unsigned long top;              /* -r */
     unsigned long max_chunk_size;   /* -k accepted, ignored */
     int block_size;                 /* -b accepted, ignored */
+    int keep_input_order;           /* --keep-input-order: report the queries of a file in file order, not by ascending length */
+    int verbose;                    /* --verbose: progress notes on stderr */
 } swg_options;
 
 void swg_parse_arguments(int argc, char **argv, swg_options *opt);

@@ -50,6 +50,7 @@ void swg_seqset_free(swg_seqset *s)
     free(s->lengths);
     free(s->offsets);
     free(s->codes);
+    free(s->input_pos);
     if (s->titles) {
         for (uint64_t i = 0; i < s->count; i++)
             free(s->titles[i]);
@@ -161,7 +162,7 @@ int swg_read_fasta(const char *path, swg_seqset *out)
         memcpy(out->titles[k], img + r->title_at, r->title_len);
         out->titles[k][r->title_len] = '\0';
     }
-    free(order);
+    out->input_pos = order;
     free(rec);
     free(img);
     if (rc) { swg_seqset_free(out); return rc; }

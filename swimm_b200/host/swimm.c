@@ -3,9 +3,17 @@
  *
  * Mirrors the reference driver (swimm.c:9-207): parse arguments, preprocess OR (load queries, load the
  * database, search, load headers, print the top hits of every query, print time / GCUPS / mode), with
- * the same stdout layout.  The search itself is the C ABI of libswimm_cuda.so (include/swimm_gpu.h);
- * with -x N the database is sharded over N GPUs and the per-GPU hit lists are merged here.
+ * the same stdout layout.  The search itself is the C ABI of libswimm_cuda.so (include/swimm_gpu.h).
+ *
+ * With -x N the database is sharded over N GPUs: one host thread per GPU uploads its shard (the reference's
+ * one-thread-per-device pattern, MICsearch.c:53,74-75), every GPU sees all queries, and the per-GPU hit lists
+ * are merged here.
+ *
+ * Streaming: `-q a,b,c` or `-q -` (file names on stdin, one per line) keeps the process and the database
+ * resident and feeds the files as batches through swg_gpu_submit / swg_gpu_poll: while batch k computes,
+ * file k+1 is parsed, uploaded and queued behind it.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -21,6 +29,133 @@ static void die_gpu(const char *what, swg_ctx *ctx, int st)
     exit(4);
 }
 
+/* ---- one host thread per GPU: context + shard upload ---- */
+typedef struct {
+    int gpu, ngpu;
+    const swg_seqset *db;
+    swg_ctx *ctx;
+    int st;
+    char err[512];
+} load_job;
+
+static void *load_thread(void *arg)
+{
+    load_job *j = (load_job *)arg;
+    j->st = swg_gpu_create(j->gpu, &j->ctx);
+    if (j->st == SWG_OK)
+        j->st = swg_gpu_load_db_offsets(j->ctx, j->db->lengths, j->db->offsets, j->db->codes, j->db->count, j->db->residues,
+                                        j->gpu, j->ngpu);
+    if (j->st != SWG_OK)
+        snprintf(j->err, sizeof(j->err), "%s", swg_gpu_last_error(j->ctx));
+    return NULL;
+}
+
+/* ---- one batch = one query file in flight ---- */
+typedef struct {
+    char *name;
+    swg_seqset q;
+    uint32_t *q_disp;
+    int *tickets;            /* one per GPU */
+    time_t when;
+    double t_submit;
+} batch;
+
+static void batch_free(batch *b)
+{
+    free(b->name);
+    free(b->q_disp);
+    free(b->tickets);
+    swg_seqset_free(&b->q);
+    memset(b, 0, sizeof(*b));
+}
+
+/* parse a query file and queue it on every GPU; returns 0, or the reference's exit code */
+static int batch_submit(batch *b, const char *qfile, swg_ctx **ctx, int ngpu, const swg_options *opt, unsigned long top)
+{
+    memset(b, 0, sizeof(*b));
+    /* queries: parsed, sorted by ascending length, encoded (reference sequences.c:223-423) */
+    if (swg_read_fasta(qfile, &b->q) != 0) {
+        printf("SWIMM: An error occurred while opening input sequence file.\n");
+        return 2;
+    }
+    b->name = strdup(qfile);
+    b->when = time(NULL);
+    b->q_disp = (uint32_t *)malloc((b->q.count + 1) * sizeof(uint32_t));
+    b->tickets = (int *)malloc((size_t)ngpu * sizeof(int));
+    for (uint64_t i = 0; i <= b->q.count; i++)
+        b->q_disp[i] = (uint32_t)b->q.offsets[i];
+    b->t_submit = swg_walltime();
+    /* every GPU gets all queries and searches its shard of the database */
+    for (int g = 0; g < ngpu; g++) {
+        int st = swg_gpu_submit(ctx[g], b->q.codes, b->q.lengths, b->q_disp, b->q.count, swg_submat_table(opt->submat),
+                                opt->open_gap, opt->extend_gap, top, &b->tickets[g]);
+        if (st != SWG_OK)
+            die_gpu("search", ctx[g], st);
+    }
+    return 0;
+}
+
+/* wait for a batch, merge the per-GPU hit lists and print the report (reference swimm.c:150-190) */
+static void batch_report(batch *b, swg_ctx **ctx, int ngpu, const swg_seqset *db, const swg_options *opt, unsigned long top)
+{
+    const uint64_t nq = b->q.count, t1 = top ? top : 1;
+    uint64_t *part_keys = (uint64_t *)calloc((size_t)ngpu * nq * t1, sizeof(uint64_t));
+    uint64_t *keys = (uint64_t *)calloc(nq * t1, sizeof(uint64_t));
+    double work = 0;
+    for (int g = 0; g < ngpu; g++) {
+        int done = 0;
+        double secs = 0;
+        int st = swg_gpu_poll(ctx[g], b->tickets[g], 1, part_keys + (size_t)g * nq * top, &secs, &done);
+        if (st != SWG_OK || !done)
+            die_gpu("result download", ctx[g], st);
+        if (secs > work)
+            work = secs;                   /* the slowest GPU, like the reference's single workTime */
+    }
+    const double wall = swg_walltime() - b->t_submit;
+    /* merge the per-GPU lists query by query */
+    uint64_t *tmp = (uint64_t *)malloc((size_t)ngpu * t1 * sizeof(uint64_t));
+    for (uint64_t i = 0; i < nq; i++) {
+        for (int g = 0; g < ngpu; g++)
+            memcpy(tmp + (size_t)g * top, part_keys + ((size_t)g * nq + i) * top, top * sizeof(uint64_t));
+        swg_merge_top_keys(tmp, ngpu, top, keys + i * top);
+    }
+    free(tmp);
+
+    printf("Query filename:\t\t\t%s\n", b->name);
+    /* queries are reported in ascending-length order like the reference (sequences.c:344); --keep-input-order reports
+     * them in the order of the file instead */
+    uint64_t *show = (uint64_t *)malloc((nq ? nq : 1) * sizeof(uint64_t));
+    for (uint64_t i = 0; i < nq; i++)
+        show[opt->keep_input_order && b->q.input_pos ? b->q.input_pos[i] : i] = i;
+    uint64_t Q = 0;
+    for (uint64_t n = 0; n < nq; n++) {
+        const uint64_t i = show[n];
+        Q += b->q.lengths[i] + (b->q.lengths[i] & 1u);      /* the reference counts odd lengths padded to even (sequences.c:370) */
+        printf("\nQuery no.\t\t\t%d\n", (int)(n + 1));
+        printf("Query description: \t\t%s\n", b->q.titles[i][0] ? b->q.titles[i] + 1 : "");
+        printf("Query length:\t\t\t%d residues\n", b->q.lengths[i]);
+        printf("\nScore\tSequence description\n");
+        for (unsigned long j = 0; j < top; j++) {
+            const uint64_t k = keys[i * top + j];
+            const char *title = db->titles[SWG_KEY_INDEX(k)];
+            printf("%d\t%s\n", SWG_KEY_SCORE(k), title[0] ? title + 1 : "");
+        }
+    }
+    free(show);
+    /* Search time: CUDA-event time of the whole batch on the slowest GPU -- wait for the query upload, profile builds,
+     * all search kernels, top-r selection and the hit-list download; the host-side merge of N x top keys is not in it
+     * (the reference's workTime covers its kernel call only, its sort is outside too: swimm.c:151-160) */
+    printf("\nSearch date:\t\t\t%s", ctime(&b->when));
+    printf("Search time:\t\t\t%lf seconds\n", work);
+    printf("Search speed:\t\t\t%.2lf GCUPS\n", ((double)Q * (double)db->residues) / (work * 1000000000.0));
+    printf("Execution mode:\t\t\tB200 GPU only (%d GPU%s, submit-to-report %lf seconds)\n", ngpu, ngpu == 1 ? "" : "s", wall);
+    printf("Profile technique:\t\tQuery Profile (shared memory)\n");
+    printf("Instruction set:\t\tsm_100a DPX s16x2 (two sequences, or two queries of a batch, per 32-bit lane), 32-bit recomputation on overflow\n");
+    fflush(stdout);
+    free(part_keys);
+    free(keys);
+}
+
 int main(int argc, char **argv)
 {
     swg_options opt;
@@ -32,8 +167,9 @@ int main(int argc, char **argv)
     printf("\nSWIMM v%s \n\n", SWG_VERSION);
     printf("Database file:\t\t\t%s\n", opt.sequences_filename);
 
+    const int from_stdin = strcmp(opt.queries_filename, "-") == 0;
     /* like the reference (swimm.c:38), an unreadable query file is reported before anything is loaded */
-    {
+    if (!from_stdin) {
         char *probe = strdup(opt.queries_filename);
         for (char *qfile = strtok(probe, ","); qfile; qfile = strtok(NULL, ",")) {
             FILE *f = fopen(qfile, "r");
@@ -63,7 +199,7 @@ int main(int argc, char **argv)
     printf("Gap open penalty:\t\t%d\n", opt.open_gap);
     printf("Gap extend penalty:\t\t%d\n", opt.extend_gap);
 
-    /* GPUs */
+    /* GPUs: one host thread each creates the context and uploads its shard */
     int visible = 0, st = swg_gpu_device_count(&visible);
     if (st != SWG_OK)
         die_gpu("GPU discovery", NULL, st);
@@ -73,89 +209,75 @@ int main(int argc, char **argv)
         return 4;
     }
     swg_ctx **ctx = (swg_ctx **)calloc((size_t)ngpu, sizeof(swg_ctx *));
+    load_job *jobs = (load_job *)calloc((size_t)ngpu, sizeof(load_job));
+    pthread_t *threads = (pthread_t *)calloc((size_t)ngpu, sizeof(pthread_t));
+    const double t_load = swg_walltime();
     for (int g = 0; g < ngpu; g++) {
-        if ((st = swg_gpu_create(g, &ctx[g])) != SWG_OK)
-            die_gpu("GPU context creation", NULL, st);
-        if ((st = swg_gpu_load_db(ctx[g], db.lengths, db.codes, db.count, db.residues, g, ngpu)) != SWG_OK)
-            die_gpu("database upload", ctx[g], st);
+        jobs[g].gpu = g;
+        jobs[g].ngpu = ngpu;
+        jobs[g].db = &db;
+        if (ngpu == 1 || pthread_create(&threads[g], NULL, load_thread, &jobs[g]) != 0) {
+            load_thread(&jobs[g]);
+            threads[g] = 0;
+        }
     }
+    for (int g = 0; g < ngpu; g++) {
+        if (threads[g])
+            pthread_join(threads[g], NULL);
+        ctx[g] = jobs[g].ctx;
+        if (jobs[g].st != SWG_OK) {
+            printf("SWIMM: database upload to GPU %d failed (%d): %s\n", g, jobs[g].st, jobs[g].err);
+            return 4;
+        }
+    }
+    if (opt.verbose)
+        fprintf(stderr, "[swimm] %d shard%s resident after %.3f s\n", ngpu, ngpu == 1 ? "" : "s", swg_walltime() - t_load);
+    free(jobs);
+    free(threads);
 
     if (swg_load_db_headers(opt.sequences_filename, &db) != 0) {
         printf("SWIMM: An error occurred while opening sequence description file.\n");
         return 3;
     }
 
-    /* -q takes one FASTA file like the reference, or several separated by commas: the database stays resident on
-     * the GPUs and every file is searched and reported in turn ("keep DB resident, stream query files") */
-    char *qlist = strdup(opt.queries_filename);
-    for (char *qfile = strtok(qlist, ","); qfile; qfile = strtok(NULL, ",")) {
-        /* queries: parsed, sorted by ascending length, encoded (reference sequences.c:223-423) */
-        swg_seqset q;
-        if (swg_read_fasta(qfile, &q) != 0) {
-            printf("SWIMM: An error occurred while opening input sequence file.\n");
-            return 2;
+    /* -q takes one FASTA file like the reference, several separated by commas, or "-" (file names on stdin): the
+     * database stays resident on the GPUs, every file is a batch, and two batches are in flight -- file k+1 is parsed,
+     * uploaded and queued while batch k computes ("keep DB resident, stream query files") */
+    batch pending, next;
+    int have_pending = 0;
+    char *qlist = from_stdin ? NULL : strdup(opt.queries_filename);
+    char *cursor = qlist, line[4096];
+    for (;;) {
+        const char *qfile = NULL;
+        if (from_stdin) {
+            if (!fgets(line, sizeof(line), stdin))
+                break;
+            line[strcspn(line, "\r\n")] = '\0';
+            if (!line[0])
+                continue;
+            qfile = line;
+        } else {
+            qfile = strtok(cursor, ",");
+            cursor = NULL;
+            if (!qfile)
+                break;
         }
-        time_t current_time = time(NULL);
-        printf("Query filename:\t\t\t%s\n", qfile);
-
-        /* search: every GPU gets all queries and its shard of the database */
-        uint32_t *q_disp = (uint32_t *)malloc((q.count + 1) * sizeof(uint32_t));
-        for (uint64_t i = 0; i <= q.count; i++)
-            q_disp[i] = (uint32_t)q.offsets[i];
-        uint64_t *part_keys = (uint64_t *)calloc((size_t)ngpu * q.count * (top ? top : 1), sizeof(uint64_t));
-        uint64_t *keys = (uint64_t *)calloc(q.count * (top ? top : 1), sizeof(uint64_t));
-        const double t0 = swg_walltime();
-        for (int g = 0; g < ngpu; g++) {
-            st = swg_gpu_set_queries(ctx[g], q.codes, q.lengths, q_disp, q.count, swg_submat_table(opt.submat), opt.open_gap,
-                                     opt.extend_gap);
-            if (st == SWG_OK)
-                st = swg_gpu_run(ctx[g], top, 0);
-            if (st != SWG_OK)
-                die_gpu("search", ctx[g], st);
+        rc = batch_submit(&next, qfile, ctx, ngpu, &opt, top);
+        if (rc != 0) {
+            if (!from_stdin)
+                return rc;
+            continue;                     /* a server keeps going when one file is unreadable */
         }
-        double work = 0;
-        for (int g = 0; g < ngpu; g++) {
-            if ((st = swg_gpu_fetch(ctx[g], NULL, part_keys + (size_t)g * q.count * top)) != SWG_OK)
-                die_gpu("result download", ctx[g], st);
-            swg_stats s;
-            swg_gpu_get_stats(ctx[g], &s);
-            if (s.search_seconds > work)
-                work = s.search_seconds;           /* the slowest GPU, like the reference's single workTime */
+        if (have_pending) {
+            batch_report(&pending, ctx, ngpu, &db, &opt, top);
+            batch_free(&pending);
         }
-        const double wall = swg_walltime() - t0;
-        /* merge the per-GPU lists query by query */
-        uint64_t *tmp = (uint64_t *)malloc((size_t)ngpu * (top ? top : 1) * sizeof(uint64_t));
-        for (uint64_t i = 0; i < q.count; i++) {
-            for (int g = 0; g < ngpu; g++)
-                memcpy(tmp + (size_t)g * top, part_keys + ((size_t)g * q.count + i) * top, top * sizeof(uint64_t));
-            swg_merge_top_keys(tmp, ngpu, top, keys + i * top);
-        }
-        free(tmp);
-        uint64_t Q = 0;
-        for (uint64_t i = 0; i < q.count; i++) {
-            Q += q.lengths[i];
-            printf("\nQuery no.\t\t\t%d\n", (int)(i + 1));
-            printf("Query description: \t\t%s\n", q.titles[i][0] ? q.titles[i] + 1 : "");
-            printf("Query length:\t\t\t%d residues\n", q.lengths[i]);
-            printf("\nScore\tSequence description\n");
-            for (unsigned long j = 0; j < top; j++) {
-                const uint64_t k = keys[i * top + j];
-                const char *title = db.titles[SWG_KEY_INDEX(k)];
-                printf("%d\t%s\n", SWG_KEY_SCORE(k), title[0] ? title + 1 : "");
-            }
-        }
-        printf("\nSearch date:\t\t\t%s", ctime(&current_time));
-        printf("Search time:\t\t\t%lf seconds\n", work);
-        printf("Search speed:\t\t\t%.2lf GCUPS\n", ((double)Q * (double)db.residues) / (work * 1000000000.0));
-        printf("Execution mode:\t\t\tB200 GPU only (%d GPU%s, end-to-end %lf seconds)\n", ngpu, ngpu == 1 ? "" : "s", wall);
-        printf("Profile technique:\t\tQuery Profile (shared memory)\n");
-        printf("Instruction set:\t\tsm_100a DPX s16x2 (two sequences, or two queries of a batch, per 32-bit lane), 32-bit recomputation on overflow\n");
-
-
-        free(q_disp);
-        free(part_keys);
-        free(keys);
-        swg_seqset_free(&q);
+        pending = next;
+        have_pending = 1;
+    }
+    if (have_pending) {
+        batch_report(&pending, ctx, ngpu, &db, &opt, top);
+        batch_free(&pending);
     }
     free(qlist);
     for (int g = 0; g < ngpu; g++)

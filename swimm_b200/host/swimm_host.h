@@ -41,6 +41,7 @@ typedef struct {
     signed char *codes;      /* [residues] codes 0..23, concatenated in the same order */
     char **titles;           /* [count] header lines WITH the leading '>' and without '\n' (may be NULL) */
     int max_title;           /* longest header line incl. '\n', +1 (reference sequences.c:41,96) */
+    uint64_t *input_pos;     /* [count] position in the input file of each (sorted) sequence; NULL for a preprocessed database */
 } swg_seqset;
 
 int swg_encode_residue(int c);                                           /* reference sequences.c:165-175 */

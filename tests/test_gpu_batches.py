@@ -47,12 +47,12 @@ def _check_keys(oracle, want, keys, top):
 
 
 def test_score_window_chunks_match_one_piece(gpu, oracle):
-    """37 queries with a 1 MB score budget on a 3000-sequence shard: 12 KB per row -> the batch is searched in several
+    """25 queries with a 1 MB score budget on a 40000-sequence shard: 160 KB per row -> the batch is searched in five
     chunks of queries (each planned, paired and top-r-selected on its own); hit lists equal the oracle's, and a fetch of
     score rows after such a run is refused."""
     from swimm_b200.gpu import SwgError
-    db, dl, dc, do = _db(3, 3000)
-    lens = list(np.random.default_rng(4).integers(20, 1400, 37))
+    db, dl, dc, do = _db(3, 40000, hi=200)
+    lens = list(np.random.default_rng(4).integers(20, 700, 25))
     ql, qc, qo = _queries(5, lens, db)
     _, dl, dc = synth.length_sorted(db)
     want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)

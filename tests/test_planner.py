@@ -97,7 +97,7 @@ def test_chain_bound_shard_prefers_the_pair_kernel_and_wider_groups():
     ql = [144, 1000, 3100, 5478]
     single, groups = check_schedule(ql, gpu.plan_describe(ql, n_sequences=8000, n_residues=91_932_856,
                                                           longest_sequence=65535))
-    assert len(groups) == 1 and set(single) == {0}
+    assert len(groups) == 1 and set(single) == set()         # the short query fills the idle lane of the stream
     # a small shard with one long sequence: a shape with more threads per sequence than the saturated optimum (G=8)
     # only when the long-tile path cannot cap the chain -- here it can, so the throughput shape stays
     single, _ = check_schedule([144], gpu.plan_describe([144], n_sequences=100_000, n_residues=35_092_341,
