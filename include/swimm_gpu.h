@@ -112,6 +112,14 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores);     /* enqueue all
 int swg_gpu_fetch(swg_ctx *ctx, int32_t *scores, uint64_t *top_keys);   /* wait + D2H */
 int swg_gpu_sync(swg_ctx *ctx);                                   /* wait only */
 
+/* ---- opt-in: alignment coordinates of the hits (no counterpart in the reference, which is score-only:
+ * CPUsearch.c:670-676; definition and tie rules: oracle/sw_oracle.c swo_align_ends) ----
+ * After swg_gpu_run / swg_gpu_fetch of the current queries with top > 0: coords[q][k][0..3] = q_start, q_end, d_start,
+ * d_end (0-based, inclusive) of an optimal alignment behind hit k of query q, in the order of swg_gpu_fetch's top_keys
+ * (this shard's hits); rows are `top` entries apart, entries without a hit hold -1.  Only the hits are aligned again
+ * (one warp each), so the cost is top alignments per query, not n. */
+int swg_gpu_align_ends(swg_ctx *ctx, int32_t *coords);
+
 /* ---- streaming: keep the database resident and feed batches as they arrive (replaces the one-shot flow of
  * swimm.c:38-160 for a long-lived process) ----
  * swg_gpu_submit enqueues the upload of a batch (copy stream), all its kernels and the download of its hit lists, and

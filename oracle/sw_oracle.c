@@ -84,6 +84,73 @@ int32_t swo_score(const int8_t *q, uint32_t m, const int8_t *d, uint32_t n,
     return best;
 }
 
+/* ---- start / end coordinates of an optimal alignment (EXTENSION: the reference is score-only, CPUsearch.c:670-676) ----
+ * PARITY UNPINNED for this function: there is no reference output to pin it to.  It restates, cell by cell, the
+ * definition the product's opt-in coordinate pass (csrc/align_ends.cu) must reproduce:
+ *   end   = the cell (i, j) of the forward recurrence above (same scores as swo_score) that holds the best score;
+ *           ties: the smallest database position j, then the smallest query position i;
+ *   start = the same search on the REVERSED prefixes q[0..i], d[0..j] (an optimal local alignment of the reversed
+ *           prefixes has the same score and ends where an optimal alignment of the originals starts), mapped back.
+ * Positions are 0-based and inclusive.  A score of 0 gives all -1.
+ * best_cell: score and argmax cell of x[0..m) vs y[0..n) read forwards (step = +1) or backwards from (x0, y0). */
+static int32_t best_cell(const int8_t *q, int64_t q0, int qstep, uint32_t m, const int8_t *d, int64_t d0, int dstep, uint32_t n,
+                         const int8_t *submat, int go, int ge, int64_t *bi, int64_t *bj)
+{
+    *bi = -1;
+    *bj = -1;
+    if (m == 0 || n == 0)
+        return 0;
+    const int32_t goe = go + ge;
+    int32_t *hrow = (int32_t *)calloc((size_t)n + 1, sizeof(int32_t));
+    int32_t *vgap = (int32_t *)calloc((size_t)n + 1, sizeof(int32_t));
+    int32_t best = 0;
+    for (uint32_t i = 0; i < m; i++) {
+        const int qi = q[q0 + (int64_t)qstep * i];
+        const int8_t *row = (qi >= 0 && qi < 23) ? submat + 32 * qi : NULL;
+        int32_t hgap = 0, diag = 0;
+        for (uint32_t j = 1; j <= n; j++) {
+            const int dj = d[d0 + (int64_t)dstep * (j - 1)];
+            const int32_t s = (row && dj >= 0 && dj < 32) ? row[dj] : 0;
+            int32_t cur = diag + s;
+            if (cur < hgap) cur = hgap;
+            if (cur < vgap[j]) cur = vgap[j];
+            if (cur < 0) cur = 0;
+            const int32_t open = cur - goe;
+            hgap -= ge;    if (hgap < open) hgap = open;
+            int32_t v = vgap[j] - ge; if (v < open) v = open;
+            vgap[j] = v;
+            diag = hrow[j];
+            hrow[j] = cur;
+            if (cur > best || (cur == best && cur > 0 && (int64_t)(j - 1) < *bj)) {
+                best = cur;
+                *bi = i;
+                *bj = j - 1;
+            }
+        }
+    }
+    free(hrow);
+    free(vgap);
+    return best;
+}
+
+int32_t swo_align_ends(const int8_t *q, uint32_t m, const int8_t *d, uint32_t n, const int8_t *submat, int go, int ge,
+                       int32_t *coords /* q_start, q_end, d_start, d_end */)
+{
+    int64_t ei, ej, si, sj;
+    const int32_t score = best_cell(q, 0, 1, m, d, 0, 1, n, submat, go, ge, &ei, &ej);
+    coords[0] = coords[1] = coords[2] = coords[3] = -1;
+    if (score <= 0)
+        return 0;
+    const int32_t back = best_cell(q, ei, -1, (uint32_t)ei + 1, d, ej, -1, (uint32_t)ej + 1, submat, go, ge, &si, &sj);
+    if (back != score)
+        return -1;              /* cannot happen: the reversed prefixes hold the same optimal alignment */
+    coords[0] = (int32_t)(ei - si);
+    coords[1] = (int32_t)ei;
+    coords[2] = (int32_t)(ej - sj);
+    coords[3] = (int32_t)ej;
+    return score;
+}
+
 /* Every query against every database sequence.
  * reference CPUsearch.c:540-548: tasks are (query, lane-group); the score of
  * sequence s for query q lands at scores[q*N + s] with s the position in the

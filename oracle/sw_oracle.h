@@ -29,6 +29,11 @@ int32_t swo_score(const int8_t *q, uint32_t m, const int8_t *d, uint32_t n,
                   const int8_t *submat, int go, int ge);
 
 /* all-vs-all: scores[qi*n_seqs + si]; queries/db are flat concatenations with prefix offsets */
+/* EXTENSION (no reference counterpart, parity unpinned): score and 0-based inclusive coordinates
+ * (q_start, q_end, d_start, d_end) of an optimal alignment; see sw_oracle.c for the tie rules. */
+int32_t swo_align_ends(const int8_t *q, uint32_t m, const int8_t *d, uint32_t n, const int8_t *submat, int go, int ge,
+                       int32_t *coords);
+
 void swo_search(const int8_t *queries, const uint32_t *q_off, uint64_t q_count,
                 const int8_t *db, const uint64_t *db_off, uint64_t n_seqs,
                 const int8_t *submat, int go, int ge, int threads, int32_t *scores);

@@ -105,7 +105,8 @@ struct swg_ctx {
     // work buffers
     DeviceBuf d_scores, d_profile, d_profile32, d_boundary, d_counters, d_resc_list, d_topk_scratch, d_top_out;
     DeviceBuf d_profile_q2, d_lines, d_resc_list2, d_q2_counters;
-    DeviceBuf d_profile_xw, d_xw_counters, d_xw_list;     // long-sequence kernel (wavefront_xw.cuh)
+    DeviceBuf d_profile_xw, d_xw_counters, d_xw_list;
+    DeviceBuf d_q_off, d_align_lines, d_coords;                      // coordinate pass (align_ends.cu)     // long-sequence kernel (wavefront_xw.cuh)
     std::vector<WorkItem> items;            // schedule of the last run
     std::vector<cudaEvent_t> item_events;   // items.size() + 1 marks
     std::vector<cudaEvent_t> chunk_events;  // two per chunk of queries, around its top-r selection
@@ -384,6 +385,9 @@ void swg_gpu_destroy(swg_ctx *ctx)
     ctx->d_profile_xw.release();
     ctx->d_xw_counters.release();
     ctx->d_xw_list.release();
+    ctx->d_q_off.release();
+    ctx->d_align_lines.release();
+    ctx->d_coords.release();
     for (cudaEvent_t ev : ctx->q_events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->item_events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
@@ -808,54 +812,95 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     if (ctx->verbose) fputs(describe_plan(ctx->q_len, main_cfgs, items).c_str(), stderr);
 
     // ---- long tiles (K3) ----
-    // A sequence is a serial chain of (columns x passes) steps of its thread group, so a very long one can outlast the
-    // whole rest of a launch.  Per work item: the first tile whose chain would come close to the estimated time of the
-    // item's launches (option long_threshold > 0: a fixed column count instead).  Those tiles leave the item's main
-    // launches and are searched, query by query, by the long-sequence kernel (wavefront_xw.cuh) on the high-priority
-    // stream, while the main launches fill the other SMs from the side stream.
+    // A warp advances its sequences one column per step, so a sequence with more columns than the warp's share of the
+    // shard outlasts the launch it is part of.  Per work item: tiles above 0.8 x (residues / warps / sequences a warp
+    // holds) are "long" (option long_threshold > 0: a fixed column count instead).  They leave the item's main launches
+    // and are searched, query by query, by the long-sequence kernel (wavefront_xw.cuh) on the high-priority stream with
+    // a few SMs of their own, while the main launches fill the other SMs from the side stream -- when the time model
+    // says that this beats keeping them (the long-sequence kernel has fewer rows per thread: lower throughput).
     std::vector<uint32_t> item_first_long(items.size(), ctx->ntiles);
+    std::vector<int> item_long_grid(items.size(), 0);
     std::vector<XwConfig> xw_cfgs(nq);
     bool any_xw = false;
     if (ctx->ntiles) {
-        const double res9 = (double)ctx->local_residues * 1e-9;
+        const double res = (double)ctx->local_residues, res9 = res * 1e-9;
+        const double total_cols = (double)ctx->h_cols_prefix[ctx->ntiles];
         for (size_t ii = 0; ii < items.size(); ++ii) {
             const WorkItem &it = items[ii];
-            double limit = 1e300;
+            const std::vector<uint32_t> qs = it.pair ? it.members : std::vector<uint32_t>(1, it.qa);
+            // the item's launches: throughput seconds on the whole shard, step seconds, sequences a warp holds at once
+            struct LaunchModel { double thr, step; int passes; double seqs_per_warp; };
+            std::vector<LaunchModel> lm;
             bool xw_ok = ctx->long_kernel != 0;
             if (it.pair) {
-                for (const Q2Launch &L : it.launches)
-                    limit = std::min(limit, long_tile_limit(2.0 * L.G * L.K / q2_rate(L.G, L.K, it.launches.size() > 1) * res9, L.K, 1));
-                for (uint32_t q : it.members) xw_ok = xw_ok && ctx->q_len[q] <= (uint32_t)kXwMaxRows;
-                if (!xw_ok) continue;          // the pair kernel keeps every tile
+                for (const Q2Launch &L : it.launches) {
+                    const double rate = q2_rate(L.G, L.K, it.launches.size() > 1);
+                    lm.push_back({2.0 * L.G * L.K / rate * res9, step_seconds_loaded(L.K, rate), 1, 32.0 / L.G});
+                }
             } else {
                 const Config &c = main_cfgs[it.qa];
-                limit = long_tile_limit((double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes) * res9, c.K, c.passes);
-                xw_ok = xw_ok && ctx->q_len[it.qa] <= (uint32_t)kXwMaxRows;
+                const double rate = shape_rate(c.G, c.K, c.passes);
+                lm.push_back({(double)c.passes * c.G * c.K / rate * res9, step_seconds_loaded(c.K, rate), (int)c.passes, 64.0 / c.G});
             }
+            for (uint32_t q : qs) xw_ok = xw_ok && ctx->q_len[q] <= (uint32_t)kXwMaxRows;
+            double limit = 1e300;
+            for (const LaunchModel &l : lm) limit = std::min(limit, 0.8 * res / ((double)warps * l.seqs_per_warp));
             uint32_t fl = ctx->ntiles;
-            if (ctx->long_cols > 0) fl = ctx->first_long_tile;
+            const bool forced = ctx->long_cols > 0;
+            if (forced) fl = ctx->first_long_tile;
             else if ((double)ctx->maxcols > 1.125 * limit)
                 fl = (uint32_t)(std::upper_bound(ctx->h_tile_cols_mono.begin(), ctx->h_tile_cols_mono.end(),
                                                  (uint32_t)std::min(limit, 4.0e9)) - ctx->h_tile_cols_mono.begin());
-            item_first_long[ii] = fl;
-            if (fl >= ctx->ntiles || !xw_ok) continue;
-            const double long_res = (double)(ctx->h_cols_prefix[ctx->ntiles] - ctx->h_cols_prefix[fl]) * kTileSeqs;
-            const std::vector<uint32_t> qs = it.pair ? it.members : std::vector<uint32_t>(1, it.qa);
-            bool all_ok = true;
-            for (uint32_t q : qs) {
-                xw_cfgs[q] = choose_xw_config(ctx->q_len[q], long_res, (double)ctx->maxcols, ctx->xw_warps, ctx->xw_rows);
-                all_ok = all_ok && xw_cfgs[q].ok();
-            }
-            if (!all_ok) {                     // (a forced shape too small for the query)
-                for (uint32_t q : qs) xw_cfgs[q] = XwConfig();
-                if (it.pair) item_first_long[ii] = ctx->ntiles;
+            if (fl >= ctx->ntiles) continue;
+            const double long_cols = total_cols - (double)ctx->h_cols_prefix[fl];
+            // outliers only: a shard that is "long" as a whole stays on the main kernels
+            if (!forced && long_cols > 0.3 * total_cols) continue;
+            if (!xw_ok) {
+                // queries the long-sequence kernel does not cover (or long_kernel = 0): a single query falls back to the
+                // 32-thread shape of its own kernel, a query group keeps every tile
+                if (!it.pair) item_first_long[ii] = fl;
                 continue;
             }
+            // SMs for the long tiles: in proportion to their share of the columns, at least kMaxLongBlocks
+            const double pairs = (double)(ctx->ntiles - fl) * kTilePairs;
+            int lg = (int)std::max<double>((double)kMaxLongBlocks, long_cols / total_cols * grid + 0.999);
+            if (fl == 0) lg = grid;
+            else lg = std::max(1, std::min(lg, grid - 1));
+            double t_xw = 0.0;
+            bool all_ok = true;
+            for (uint32_t q : qs) {
+                xw_cfgs[q] = choose_xw_config(ctx->q_len[q], pairs, long_cols * kTilePairs, (double)ctx->maxcols, lg, ctx->xw_warps,
+                                              ctx->xw_rows);
+                all_ok = all_ok && xw_cfgs[q].ok();
+                t_xw += xw_cfgs[q].seconds;
+            }
+            if (all_ok && !forced) {
+                // keep the tiles when the split is not expected to pay
+                const double last_main = fl ? (double)ctx->h_tile_cols_mono[fl - 1] : 0.0;
+                const double main_share = (1.0 - long_cols / total_cols) * grid / std::max(1, grid - lg);
+                double t_keep = 0.0, t_split = 0.0;
+                for (const LaunchModel &l : lm) {
+                    t_keep += std::max(l.thr, (double)ctx->maxcols * l.passes * l.step);
+                    t_split += std::max(l.thr * main_share, last_main * l.passes * l.step);
+                }
+                t_split = std::max(t_split, t_xw);
+                if (ctx->verbose)
+                    fprintf(stderr, "[swg] item %zu: tiles %u.. long (limit %.0f columns): keep %.3f ms, split %.3f ms (long-sequence kernel %.3f ms on %d SMs)\n",
+                            ii, fl, limit, t_keep * 1e3, t_split * 1e3, t_xw * 1e3, lg);
+                if (t_split >= 0.97 * t_keep) all_ok = false;
+            }
+            if (!all_ok) {                     // (or a forced shape too small for the query)
+                for (uint32_t q : qs) xw_cfgs[q] = XwConfig();
+                if (!it.pair && forced) item_first_long[ii] = fl;      // forced threshold: the 32-thread shape
+                continue;
+            }
+            item_first_long[ii] = fl;
+            item_long_grid[ii] = lg;
             any_xw = true;
             if (ctx->verbose)
                 for (uint32_t q : qs)
-                    fprintf(stderr, "[swg] query %u (%u rows): tiles %u..%u (%.0f columns x 16) on the long-sequence kernel, %d warps x %d rows\n",
-                            q, (unsigned)ctx->q_len[q], fl, ctx->ntiles - 1, long_res / kTileSeqs, xw_cfgs[q].W, xw_cfgs[q].K);
+                    fprintf(stderr, "[swg] query %u (%u rows): tiles %u..%u (%.0f columns x 16) on the long-sequence kernel, %d warps x %d rows, %d pairs per CTA, %d CTAs\n",
+                            q, (unsigned)ctx->q_len[q], fl, ctx->ntiles - 1, long_cols, xw_cfgs[q].W, xw_cfgs[q].K, xw_cfgs[q].groups, lg);
         }
     }
 
@@ -910,6 +955,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             if (!xc.ok()) return;
             w.profile = ctx->d_profile_xw.as<uint8_t>();
             w.xw_warps = (uint32_t)xc.W;
+            w.xw_groups = (uint32_t)xc.groups;
             if (we == cudaSuccess && fresh((2u << 20) + (uint32_t)xc.K)) we = launch_xw_l16(xc.K, 1, ctx->stream, w);
             if (we == cudaSuccess && fresh((3u << 20) + (uint32_t)xc.K)) we = launch_xw_l32(xc.K, 1, ctx->stream, w);
         };
@@ -1017,6 +1063,9 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         x.resc_count = xcnt + 1;
         x.resc_list = ctx->d_xw_list.as<uint32_t>();
         x.xw_warps = (uint32_t)xc.W;
+        x.xw_groups = (uint32_t)xc.groups;
+        // no more CTAs than there are pairs to keep their groups busy
+        xgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)xgrid, ((uint64_t)x.tile_count * kTilePairs + xc.groups - 1) / xc.groups));
         e = launch_xw_l16(xc.K, xgrid, st, x);
         x.task_counter = xcnt + 2;
         if (e == cudaSuccess) e = launch_xw_l32(xc.K, xgrid, st, x);
@@ -1071,11 +1120,8 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                     forked = e == cudaSuccess;
                     if (forked) ks = ctx->side_stream;
                 }
-                for (size_t k = 0; k < it.members.size() && e == cudaSuccess; ++k) {
-                    const uint32_t q = it.members[k];
-                    const uint64_t groups = ((uint64_t)(ctx->ntiles - main_tiles) * kTilePairs * xw_cfgs[q].W + 15) / 16;
-                    e = enqueue_xw(q, main_tiles, long_grid_for(main_tiles, groups, main_tiles > 0), ctx->stream);
-                }
+                for (size_t k = 0; k < it.members.size() && e == cudaSuccess; ++k)
+                    e = enqueue_xw(it.members[k], main_tiles, item_long_grid[ii], ctx->stream);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "long-sequence kernel launch");
             }
             auto lane_q = [&](const LaneSlice &sl) { return sl.q >= 0 ? ctx->d_queries.as<int8_t>() + ctx->q_off[sl.q] : nullptr; };
@@ -1180,8 +1226,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 forked = e == cudaSuccess;
             }
             if (use_xw) {
-                const uint64_t groups = ((uint64_t)long_tiles * kTilePairs * xw_cfgs[q].W + 15) / 16;
-                if (e == cudaSuccess) e = enqueue_xw(q, first_long, long_grid_for(first_long, groups, main_tiles > 0), ctx->stream);
+                if (e == cudaSuccess) e = enqueue_xw(q, first_long, item_long_grid[ii], ctx->stream);
             } else {
                 const uint64_t long_warps = (uint64_t)long_tiles * kTilePairs;          // one pair per warp at G = 32
                 const int long_grid = long_grid_for(first_long, (long_warps + warps_per_block - 1) / warps_per_block, main_tiles > 0);
@@ -1326,6 +1371,35 @@ int swg_gpu_search(swg_ctx *ctx, const signed char *queries, const uint16_t *q_l
     if (st == SWG_OK) st = swg_gpu_fetch(ctx, scores, top_keys);
     if (st == SWG_OK && work_seconds) *work_seconds = ctx->stats.search_seconds;
     return st;
+}
+
+// ---- opt-in: where the alignments behind the hits start and end --------------------------------------------
+int swg_gpu_align_ends(swg_ctx *ctx, int32_t *coords)
+{
+    if (!ctx || !coords) return fail(ctx, SWG_ERR_ARG, "NULL argument");
+    if (!ctx->run_done || !ctx->queries_ready) return fail(ctx, SWG_ERR_STATE, "swg_gpu_align_ends needs a completed swg_gpu_run of the current queries");
+    SWG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nq = ctx->q_count, top = ctx->run_top, stride = ctx->run_top_stride;
+    for (uint64_t i = 0; i < nq * stride * 4; ++i) coords[i] = -1;
+    if (!nq || !top || !ctx->ntiles) return SWG_OK;
+    const uint64_t line_stride = ctx->maxcols;
+    const uint64_t line_bytes = nq * top * line_stride * sizeof(int2);
+    if (line_bytes > (8ull << 30)) return fail(ctx, SWG_ERR_ARG, "%llu hits x %llu columns: too many for the coordinate pass",
+                                                (unsigned long long)(nq * top), (unsigned long long)line_stride);
+    SWG_CUDA(ctx, ctx->d_q_off.reserve((nq + 1) * sizeof(uint32_t)));
+    SWG_CUDA(ctx, ctx->d_align_lines.reserve(line_bytes));
+    SWG_CUDA(ctx, ctx->d_coords.reserve(nq * top * 4 * sizeof(int32_t)));
+    SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_q_off.p, ctx->q_off.data(), (nq + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = launch_align_ends(ctx->d_top_out.as<uint64_t>(), nq, top, ctx->d_queries.as<int8_t>(), ctx->d_q_off.as<uint32_t>(),
+                                      ctx->d_submat.as<int8_t>(), ctx->open_gap + ctx->extend_gap, ctx->extend_gap,
+                                      ctx->d_db.as<uint4>(), ctx->d_tile_off.as<uint64_t>(), ctx->d_tile_cols.as<uint32_t>(),
+                                      ctx->num_shards, ctx->d_align_lines.as<int2>(), (uint32_t)line_stride,
+                                      ctx->d_coords.as<int32_t>(), ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "coordinate pass launch");
+    SWG_CUDA(ctx, cudaMemcpy2DAsync(coords, stride * 4 * sizeof(int32_t), ctx->d_coords.p, top * 4 * sizeof(int32_t),
+                                    top * 4 * sizeof(int32_t), nq, cudaMemcpyDeviceToHost, ctx->stream));
+    SWG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWG_OK;
 }
 
 // ---- streaming: two batches in flight ----------------------------------------------------------------

@@ -80,6 +80,7 @@ struct WfParams {
     uint32_t lane_flags;          // kLaneActive / kLaneFirst bits, low lane in bits 0-1, high lane in bits 2-3
     // long-sequence kernel (wavefront_xw.cuh) only
     uint32_t xw_warps;            // W: warps (= concurrent passes) per sequence pair, 1, 2, 4, 8 or 16
+    uint32_t xw_groups;           // sequence pairs a CTA works on at the same time (<= 16 / W)
 };
 constexpr uint32_t kLaneActive = 1u;   // the lane holds a query: its scores are stored
 constexpr uint32_t kLaneFirst = 2u;    // ... and this launch is the query's first pass (nothing to merge with)

@@ -40,6 +40,13 @@ cudaError_t launch_topk(const TopkPlan &plan, const int32_t *d_scores, uint64_t 
                         uint32_t shard, uint32_t num_shards, uint64_t *d_scratch, uint64_t *d_out, cudaStream_t stream,
                         uint64_t *launches);
 
+// align_ends.cu: start / end coordinates of the alignments behind the hit keys d_keys[q_count][top] (opt-in pass);
+// d_lines: [q_count * top][line_stride] scratch, d_coords: [q_count][top][4] = q_start, q_end, d_start, d_end (0-based)
+cudaError_t launch_align_ends(const uint64_t *d_keys, uint64_t q_count, uint64_t top, const int8_t *d_queries,
+                              const uint32_t *d_q_off, const int8_t *d_submat, int goe, int ge, const uint4 *d_db,
+                              const uint64_t *d_tile_off, const uint32_t *d_tile_cols, uint32_t num_shards, int2 *d_lines,
+                              uint32_t line_stride, int32_t *d_coords, cudaStream_t stream);
+
 // pipebench.cu: measured issue rates of the kernel's instruction mix (the roofline denominator)
 int pipebench_probe_count();
 const char *pipebench_probe_name(int probe);

@@ -176,30 +176,33 @@ Config wide_config(uint32_t m)
     return c;
 }
 
-// cycles one column costs a thread group on a busy SM: about 24 per row plus the per-column bookkeeping (measured on the
-// long-sequence workload); the serial chain of a sequence is its columns times this
-static double step_cycles(int K) { return 24.0 * K + 100.0; }
+constexpr double kGpuWarps = 148.0 * 16.0;      // resident warps the rate tables were measured with
 
-double long_tile_limit(double seconds, int K, uint32_t passes)
-{
-    return 0.8 * seconds * kSmHz / (step_cycles(K) * passes);
-}
+double step_seconds_loaded(int K, double rate_gcups) { return 64.0 * K * kGpuWarps / (rate_gcups * 1e9); }
+double step_seconds_alone(int K) { return (26.0 * K + 120.0) / kSmHz; }
+double xw_rate(int K) { return kRateXw[K]; }
 
-XwConfig choose_xw_config(uint32_t m, double residues, double maxcols, long force_warps, long force_rows)
+XwConfig choose_xw_config(uint32_t m, double pairs, double pair_columns, double maxcols, int ctas, long force_warps,
+                          long force_rows)
 {
     XwConfig best;
     if (m == 0) m = 1;
+    if (ctas < 1) ctas = 1;
     double best_cost = 1e300;
     for (int W = 1; W <= 16; W *= 2)
         for (int K = 1; K <= kMaxRowsPerThread; ++K) {
             if ((force_warps && W != force_warps) || (force_rows && K != force_rows)) continue;
             if ((uint32_t)(W * 32 * K) < m) continue;
             if (W * ((K + 15) / 16) > 16) continue;                 // W passes of 12.5 KB (K <= 16) or 25 KB in shared memory
-            // throughput: the rows computed at the multi-pass rate of the sequence-pair kernel (same inner loop)
-            const double thr = (double)W * 32 * K / shape_rate(32, K, 2) * residues * 1e-9;
-            const double chain = (maxcols + 40.0 * W) * step_cycles(K) / kSmHz;
-            const double c = std::max(thr, chain) + 1e-3 * thr + 1e-3 * chain;
-            if (c < best_cost) { best_cost = c; best.K = K; best.W = W; }
+            for (int groups = 16 / W; groups >= 1; groups /= 2) {
+                // a step is issue-bound when the SM's 16 warp slots are busy and latency-bound when few warps run
+                const double active = (double)groups * W;
+                const double step = std::max(step_seconds_alone(K), step_seconds_loaded(K, xw_rate(K)) * active / 16.0);
+                const double slots = (double)ctas * groups;         // pairs in flight
+                const double per_slot = std::max(pair_columns / slots, std::min(pairs, 1.0) * (maxcols + 40.0 * W));
+                const double c = per_slot * step * (1.0 + 1e-3 * K);          // ties: fewer rows per thread
+                if (c < best_cost) { best_cost = c; best.K = K; best.W = W; best.groups = groups; best.seconds = per_slot * step; }
+            }
         }
     return best;
 }

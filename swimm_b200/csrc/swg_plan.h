@@ -23,6 +23,8 @@ struct Config {          // how one query is mapped onto thread groups
 struct XwConfig {        // how one query is mapped onto the long-sequence kernel (wavefront_xw.cuh)
     int K = 0;           // rows per thread
     int W = 0;           // warps (= concurrent passes of 32*K rows) per sequence pair; 0: the query does not fit (> 8192 rows)
+    int groups = 0;      // sequence pairs a CTA works on at the same time (<= 16 / W): fewer groups = shorter steps
+    double seconds = 0;  // estimated run time on `ctas` SMs
     bool ok() const { return W > 0; }
 };
 
@@ -74,12 +76,17 @@ double q2_rate(int G, int K, bool multi);
 Config choose_config(uint32_t m, double residues, double maxcols, long force_group, long force_rows);
 Config wide_config(uint32_t m);
 
+// Time model of a sequence's serial chain.  A warp advances its sequences one column per STEP; on a busy SM (16 warps)
+// a step of K rows takes 64 * K cells / (the kernel's measured rate per warp), on a nearly idle SM it is bounded by the
+// dependent instruction chain instead (about 26 cycles per row + 120 per column).
+double step_seconds_loaded(int K, double rate_gcups);
+double step_seconds_alone(int K);
+double xw_rate(int K);
 // long-sequence kernel: W warps x 32 threads x K rows >= m with the profile of all W passes in shared memory; the shape
-// that minimises max(throughput time of `residues` residues, serial chain of a sequence of `maxcols` columns)
-XwConfig choose_xw_config(uint32_t m, double residues, double maxcols, long force_warps = 0, long force_rows = 0);
-// columns above which a sequence's serial chain (one column per step of K rows, `passes` times) would come close to a
-// launch that takes `seconds`: such tiles go to the long-sequence kernel
-double long_tile_limit(double seconds, int K, uint32_t passes);
+// and the number of concurrent pairs per CTA that minimise the estimated time of `pairs` sequence pairs with
+// `pair_columns` columns in total, the longest `maxcols` columns, on `ctas` SMs
+XwConfig choose_xw_config(uint32_t m, double pairs, double pair_columns, double maxcols, int ctas, long force_warps = 0,
+                          long force_rows = 0);
 
 // query-pair kernel: launch heights covering m rows; the two lanes as streams of queries
 PairConfig choose_pair_config(uint32_t m, long force_group, long force_rows);

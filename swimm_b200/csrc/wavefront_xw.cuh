@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_xw_kernel(const Wf
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t w = warp % W;                      // this warp's pass
     const uint32_t grp = warp / W;
+    if (grp >= p.xw_groups) return;                   // fewer pairs per CTA = fewer warps per scheduler = shorter steps
     const bool has_in = w > 0, has_out = w + 1 < W;
     // the last-row rings live behind the profile: no long-latency load is ever outstanding when a step count is
     // published (the release store's fence would wait for it)

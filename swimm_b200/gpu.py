@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "swg_gpu_set_queries", "swg_gpu_run", "swg_gpu_fetch", "swg_gpu_sync", "swg_gpu_get_stats", "swg_gpu_get_query_seconds",
     "swg_gpu_get_query_kernels", "swg_plan_describe", "swg_gpu_pipebench",
     "swg_gpu_set_option", "swg_gpu_debug_read", "swimm_gpu_search_avx2_compat", "swg_gpu_submit", "swg_gpu_poll",
-    "swg_gpu_load_db_offsets",
+    "swg_gpu_load_db_offsets", "swg_gpu_align_ends",
 ]
 
 
@@ -76,6 +76,7 @@ def load_library() -> C.CDLL:
     L.swg_gpu_pipebench.argtypes = [vp, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.swg_gpu_debug_read.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     L.swg_gpu_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.swg_gpu_align_ends.argtypes = [vp, vp]
     L.swg_gpu_submit.argtypes = [vp, vp, vp, vp, u64, vp, i32, i32, u64, C.POINTER(i32)]
     L.swg_gpu_poll.argtypes = [vp, i32, i32, vp, C.POINTER(C.c_double), C.POINTER(i32)]
     L.swimm_gpu_search_avx2_compat.argtypes = [vp, vp, C.c_ulong, vp, vp, vp, vp, C.c_ulong, vp, vp, i32, i32, i32, i32,
@@ -219,6 +220,12 @@ class GpuSearch:
         self.set_queries(q_codes, q_lengths, q_disp, submat, go, ge)
         self.run(top, want_scores)
         return self.fetch(want_scores, top > 0)
+
+    def align_ends(self) -> np.ndarray:
+        """Opt-in coordinate pass after a search with top > 0: [q][top][4] = q_start, q_end, d_start, d_end (0-based)."""
+        out = np.full((self.q_count, self.top, 4), -1, dtype=np.int32)
+        self._check(self.L.swg_gpu_align_ends(self.ctx, out.ctypes.data), "align_ends")
+        return out
 
     def submit(self, q_codes, q_lengths, q_disp, submat, go, ge, top) -> int:
         """Streaming: enqueue a whole batch (upload, kernels, hit-list download) and return a ticket at once; two

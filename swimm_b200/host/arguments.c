@@ -49,6 +49,9 @@ static struct argp_option options[] = {
      "reports (it sorts the queries, sequences.c:344; its own lengths array is copied before that sort, :276, so it "
      "requires multi-query files that are already sorted -- this build accepts any order).", 3},
     {"verbose", 1002, 0, 0, "Progress notes on stderr.", 3},
+    {"coordinates", 1003, 0, 0,
+     "Also print, for every hit, the query range and the sequence range (1-based) of an optimal alignment.  An "
+     "extension: the reference reports scores only; without this flag the output keeps the reference's layout.", 3},
     {0}};
 
 typedef struct {
@@ -125,6 +128,7 @@ static int parse_opt(int key, char *arg, struct argp_state *state)
     case 'b': o->block_size = atoi(arg); break;
     case 1001: o->keep_input_order = 1; break;
     case 1002: o->verbose = 1; break;
+    case 1003: o->coordinates = 1; break;
     case ARGP_KEY_END:
         if (ps->argc == 1)
             argp_failure(state, 1, 0, "Missing options");

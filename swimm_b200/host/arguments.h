@@ -30,6 +30,7 @@ typedef struct {
     int block_size;                 /* -b accepted, ignored */
     int keep_input_order;           /* --keep-input-order: report the queries of a file in file order, not by ascending length */
     int verbose;                    /* --verbose: progress notes on stderr */
+    int coordinates;                /* --coordinates: print the query / sequence range of every hit's alignment (extension) */
 } swg_options;
 
 void swg_parse_arguments(int argc, char **argv, swg_options *opt);

@@ -58,6 +58,10 @@ typedef struct {
     int *tickets;            /* one per GPU */
     time_t when;
     double t_submit;
+    /* --coordinates: the batch is searched with the blocking calls and keeps its per-GPU results here */
+    uint64_t *part_keys;     /* [ngpu][q][top] */
+    int32_t *part_coords;    /* [ngpu][q][top][4] */
+    double work;
 } batch;
 
 static void batch_free(batch *b)
@@ -65,6 +69,8 @@ static void batch_free(batch *b)
     free(b->name);
     free(b->q_disp);
     free(b->tickets);
+    free(b->part_keys);
+    free(b->part_coords);
     swg_seqset_free(&b->q);
     memset(b, 0, sizeof(*b));
 }
@@ -85,6 +91,32 @@ static int batch_submit(batch *b, const char *qfile, swg_ctx **ctx, int ngpu, co
     for (uint64_t i = 0; i <= b->q.count; i++)
         b->q_disp[i] = (uint32_t)b->q.offsets[i];
     b->t_submit = swg_walltime();
+    if (opt->coordinates) {
+        /* opt-in coordinate pass: blocking calls (search on every GPU first, then results + coordinates per GPU) */
+        const uint64_t nq = b->q.count, t1 = top ? top : 1;
+        b->part_keys = (uint64_t *)calloc((size_t)ngpu * nq * t1, sizeof(uint64_t));
+        b->part_coords = (int32_t *)calloc((size_t)ngpu * nq * t1 * 4, sizeof(int32_t));
+        for (int g = 0; g < ngpu; g++) {
+            int st = swg_gpu_set_queries(ctx[g], b->q.codes, b->q.lengths, b->q_disp, nq, swg_submat_table(opt->submat),
+                                         opt->open_gap, opt->extend_gap);
+            if (st == SWG_OK)
+                st = swg_gpu_run(ctx[g], top, 0);
+            if (st != SWG_OK)
+                die_gpu("search", ctx[g], st);
+        }
+        for (int g = 0; g < ngpu; g++) {
+            int st = swg_gpu_fetch(ctx[g], NULL, b->part_keys + (size_t)g * nq * top);
+            swg_stats ss;
+            swg_gpu_get_stats(ctx[g], &ss);
+            if (ss.device_seconds > b->work)
+                b->work = ss.device_seconds;
+            if (st == SWG_OK)
+                st = swg_gpu_align_ends(ctx[g], b->part_coords + (size_t)g * nq * top * 4);
+            if (st != SWG_OK)
+                die_gpu("result download", ctx[g], st);
+        }
+        return 0;
+    }
     /* every GPU gets all queries and searches its shard of the database */
     for (int g = 0; g < ngpu; g++) {
         int st = swg_gpu_submit(ctx[g], b->q.codes, b->q.lengths, b->q_disp, b->q.count, swg_submat_table(opt->submat),
@@ -99,10 +131,10 @@ static int batch_submit(batch *b, const char *qfile, swg_ctx **ctx, int ngpu, co
 static void batch_report(batch *b, swg_ctx **ctx, int ngpu, const swg_seqset *db, const swg_options *opt, unsigned long top)
 {
     const uint64_t nq = b->q.count, t1 = top ? top : 1;
-    uint64_t *part_keys = (uint64_t *)calloc((size_t)ngpu * nq * t1, sizeof(uint64_t));
+    uint64_t *part_keys = b->part_keys ? b->part_keys : (uint64_t *)calloc((size_t)ngpu * nq * t1, sizeof(uint64_t));
     uint64_t *keys = (uint64_t *)calloc(nq * t1, sizeof(uint64_t));
-    double work = 0;
-    for (int g = 0; g < ngpu; g++) {
+    double work = b->work;
+    for (int g = 0; g < ngpu && !b->part_keys; g++) {
         int done = 0;
         double secs = 0;
         int st = swg_gpu_poll(ctx[g], b->tickets[g], 1, part_keys + (size_t)g * nq * top, &secs, &done);
@@ -134,10 +166,24 @@ static void batch_report(batch *b, swg_ctx **ctx, int ngpu, const swg_seqset *db
         printf("\nQuery no.\t\t\t%d\n", (int)(n + 1));
         printf("Query description: \t\t%s\n", b->q.titles[i][0] ? b->q.titles[i] + 1 : "");
         printf("Query length:\t\t\t%d residues\n", b->q.lengths[i]);
-        printf("\nScore\tSequence description\n");
+        printf(b->part_coords ? "\nScore\tQuery range\tSequence range\tSequence description\n" : "\nScore\tSequence description\n");
         for (unsigned long j = 0; j < top; j++) {
             const uint64_t k = keys[i * top + j];
             const char *title = db->titles[SWG_KEY_INDEX(k)];
+            if (b->part_coords) {
+                /* --coordinates: query and database range of an optimal alignment, 1-based inclusive; the hit's
+                 * coordinates sit beside its key in the list of the GPU that found it */
+                const int32_t *c = NULL;
+                for (int g = 0; g < ngpu && !c; g++)
+                    for (unsigned long jj = 0; jj < top && !c; jj++)
+                        if (part_keys[((size_t)g * nq + i) * top + jj] == k)
+                            c = b->part_coords + (((size_t)g * nq + i) * top + jj) * 4;
+                if (c && c[0] >= 0)
+                    printf("%d\t%d-%d\t%d-%d\t%s\n", SWG_KEY_SCORE(k), c[0] + 1, c[1] + 1, c[2] + 1, c[3] + 1, title[0] ? title + 1 : "");
+                else
+                    printf("%d\t-\t-\t%s\n", SWG_KEY_SCORE(k), title[0] ? title + 1 : "");
+                continue;
+            }
             printf("%d\t%s\n", SWG_KEY_SCORE(k), title[0] ? title + 1 : "");
         }
     }
@@ -152,7 +198,8 @@ static void batch_report(batch *b, swg_ctx **ctx, int ngpu, const swg_seqset *db
     printf("Profile technique:\t\tQuery Profile (shared memory)\n");
     printf("Instruction set:\t\tsm_100a DPX s16x2 (two sequences, or two queries of a batch, per 32-bit lane), 32-bit recomputation on overflow\n");
     fflush(stdout);
-    free(part_keys);
+    if (!b->part_keys)
+        free(part_keys);
     free(keys);
 }
 

@@ -85,6 +85,8 @@ class Oracle:
         L.swo_sort_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.swo_top.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.swo_length_order.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.swo_align_ends.restype = C.c_int32
+        L.swo_align_ends.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 
     def encode_residue(self, c):
         return self.L.swo_encode_residue(int(c))
@@ -94,6 +96,15 @@ class Oracle:
         d = np.ascontiguousarray(d, np.int8)
         submat = np.ascontiguousarray(submat, np.int8)
         return self.L.swo_score(q.ctypes.data, len(q), d.ctypes.data, len(d), submat.ctypes.data, go, ge)
+
+    def align_ends(self, q, d, submat, go, ge):
+        """EXTENSION (no reference counterpart): (score, [q_start, q_end, d_start, d_end]) 0-based inclusive."""
+        q = np.ascontiguousarray(q, np.int8)
+        d = np.ascontiguousarray(d, np.int8)
+        submat = np.ascontiguousarray(submat, np.int8)
+        c = np.zeros(4, np.int32)
+        s = self.L.swo_align_ends(q.ctypes.data, len(q), d.ctypes.data, len(d), submat.ctypes.data, go, ge, c.ctypes.data)
+        return s, c
 
     def search(self, q_codes, q_off, db_codes, db_off, submat, go, ge, threads=0):
         q_codes = np.ascontiguousarray(q_codes, np.int8)

@@ -132,3 +132,44 @@ def test_reference_signature_entry_on_all_gpus(oracle):
                                          n_threads=n_threads)
         assert np.array_equal(scores[:, :db.n], want), n_threads
         assert (scores[:, db.n:] == 0).all()
+
+
+def test_alignment_coordinates_of_the_hits(gpu, oracle):
+    """Opt-in coordinate pass (no counterpart in the reference, which is score-only): for every hit of every query the
+    start and end of an optimal alignment as oracle.align_ends defines them (ties: smallest database position, then
+    smallest query position; start from the reversed prefixes).  Planted fragments, repeats with many tied cells,
+    a query longer than a strip of 32 rows, hits in long sequences, two shards."""
+    from swimm_b200.gpu import split_key
+    rng = np.random.default_rng(17)
+    q = synth.make_queries(rng, [9, 31, 33, 150, 700])
+    q.residues[q.offsets[0]:q.offsets[1]] = ord("W")                      # WWWWWWWWW: every cell of a W run ties
+    lens = np.concatenate([synth.lognormal_lengths(rng, 400, 4.8, 0.7, 1, 900), [3000, 5000]])
+    db = synth.make_seqset(rng, lens)
+    synth.plant(rng, db, q, fraction=0.2, frag_range=(5, 600), rate=0.1)
+    db.residues[db.offsets[400] + 100:db.offsets[400] + 140] = ord("W")   # a W run inside a long sequence
+    db.residues[db.offsets[7]:db.offsets[8]] = ord("W")
+    _, dl, dc = synth.length_sorted(db)
+    _, ql, qc = synth.length_sorted(q)
+    do = np.zeros(db.n + 1, np.uint64)
+    np.cumsum(dl.astype(np.uint64), out=do[1:])
+    qo = np.zeros(q.n + 1, np.uint32)
+    np.cumsum(ql.astype(np.uint32), out=qo[1:])
+    b62 = host.submat("blosum62")
+    for shard, shards in [(0, 1), (1, 2)]:
+        gpu.load_db(dl, dc, shard=shard, num_shards=shards)
+        _, keys = gpu.search(qc, ql, qo[:-1], b62, 10, 2, 8)
+        coords = gpu.align_ends()
+        assert coords.shape == (q.n, 8, 4)
+        checked = 0
+        for qi in range(q.n):
+            ks, ki = split_key(keys[qi])
+            for h in range(8):
+                if ks[h] == 0:
+                    assert (coords[qi, h] == -1).all()
+                    continue
+                d = dc[int(do[ki[h]]):int(do[ki[h] + 1])]
+                s, c = oracle.align_ends(qc[qo[qi]:qo[qi + 1]], d, b62, 10, 2)
+                assert s == ks[h] and np.array_equal(coords[qi, h], c), (shard, qi, h, ks[h], coords[qi, h], c)
+                assert 0 <= c[0] <= c[1] < ql[qi] and 0 <= c[2] <= c[3] < dl[ki[h]]
+                checked += 1
+        assert checked >= 30
