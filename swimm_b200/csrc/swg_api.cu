@@ -866,16 +866,38 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             int lg = (int)std::max<double>((double)kMaxLongBlocks, long_cols / total_cols * grid + 0.999);
             if (fl == 0) lg = grid;
             else lg = std::max(1, std::min(lg, grid - 1));
-            double t_xw = 0.0;
+            // per query: the long-sequence kernel, or -- queries of one pass (<= 1024 rows) -- the 32-thread single-pass
+            // shape of the sequence-pair kernel when the same time model favours it (short queries: the cross-warp
+            // wavefront has too few rows per thread to pay for its hand-off)
+            double t_long = 0.0;
             bool all_ok = true;
             for (uint32_t q : qs) {
-                xw_cfgs[q] = choose_xw_config(ctx->q_len[q], pairs, long_cols * kTilePairs, (double)ctx->maxcols, lg, ctx->xw_warps,
-                                              ctx->xw_rows);
-                all_ok = all_ok && xw_cfgs[q].ok();
-                t_xw += xw_cfgs[q].seconds;
+                const uint32_t m = std::max<uint32_t>(ctx->q_len[q], 1);
+                XwConfig xc = choose_xw_config(m, pairs, long_cols * kTilePairs, (double)ctx->maxcols, lg, ctx->xw_warps, ctx->xw_rows);
+                if (m <= (uint32_t)kMaxPassRows && !ctx->xw_warps && !ctx->xw_rows) {
+                    const int K = (int)((m + 31) / 32);
+                    const double active = std::min(16.0, std::max(1.0, pairs / lg));
+                    const double step = std::max(step_seconds_alone(K), step_seconds_loaded(K, shape_rate(32, K, 1)) * active / 16.0);
+                    const double t_wide = std::max(long_cols * kTilePairs / (lg * 16.0), (double)ctx->maxcols) * step;
+                    if (!xc.ok() || t_wide < xc.seconds) {
+                        xc = XwConfig();
+                        xc.K = K;
+                        xc.W = 1;
+                        xc.groups = 16;
+                        xc.wide = true;
+                        xc.seconds = t_wide;
+                    }
+                }
+                xw_cfgs[q] = xc;
+                all_ok = all_ok && xc.ok();
+                t_long += xc.seconds;
             }
-            if (all_ok && !forced) {
-                // keep the tiles when the split is not expected to pay
+            if (all_ok && !it.pair && xw_cfgs[it.qa].wide) {
+                const Config &c = main_cfgs[it.qa];
+                if (c.G == 32 && c.passes == 1 && c.K == xw_cfgs[it.qa].K) all_ok = false;       // the main shape IS that shape
+            }
+            if (ctx->verbose) {
+                // what the time model expects (reported only: the split itself follows the column limit)
                 const double last_main = fl ? (double)ctx->h_tile_cols_mono[fl - 1] : 0.0;
                 const double main_share = (1.0 - long_cols / total_cols) * grid / std::max(1, grid - lg);
                 double t_keep = 0.0, t_split = 0.0;
@@ -883,13 +905,10 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                     t_keep += std::max(l.thr, (double)ctx->maxcols * l.passes * l.step);
                     t_split += std::max(l.thr * main_share, last_main * l.passes * l.step);
                 }
-                t_split = std::max(t_split, t_xw);
-                if (ctx->verbose)
-                    fprintf(stderr, "[swg] item %zu: tiles %u.. long (limit %.0f columns): keep %.3f ms, split %.3f ms (long-sequence kernel %.3f ms on %d SMs)\n",
-                            ii, fl, limit, t_keep * 1e3, t_split * 1e3, t_xw * 1e3, lg);
-                if (t_split >= 0.97 * t_keep) all_ok = false;
+                fprintf(stderr, "[swg] item %zu: tiles %u.. long (limit %.0f columns): model keep %.3f ms, split %.3f ms main + %.3f ms long tiles on %d SMs\n",
+                        ii, fl, limit, t_keep * 1e3, t_split * 1e3, t_long * 1e3, lg);
             }
-            if (!all_ok) {                     // (or a forced shape too small for the query)
+            if (!all_ok) {                     // (a forced shape too small for the query, or nothing to gain)
                 for (uint32_t q : qs) xw_cfgs[q] = XwConfig();
                 if (!it.pair && forced) item_first_long[ii] = fl;      // forced threshold: the 32-thread shape
                 continue;
@@ -899,8 +918,10 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             any_xw = true;
             if (ctx->verbose)
                 for (uint32_t q : qs)
-                    fprintf(stderr, "[swg] query %u (%u rows): tiles %u..%u (%.0f columns x 16) on the long-sequence kernel, %d warps x %d rows, %d pairs per CTA, %d CTAs\n",
-                            q, (unsigned)ctx->q_len[q], fl, ctx->ntiles - 1, long_cols, xw_cfgs[q].W, xw_cfgs[q].K, xw_cfgs[q].groups, lg);
+                    fprintf(stderr, "[swg] query %u (%u rows): tiles %u..%u (%.0f columns x 16) on %s, %d warps x %d rows, %d pairs per CTA, %d CTAs\n",
+                            q, (unsigned)ctx->q_len[q], fl, ctx->ntiles - 1, long_cols,
+                            xw_cfgs[q].wide ? "the 32-thread shape of the sequence-pair kernel" : "the long-sequence kernel", xw_cfgs[q].W,
+                            xw_cfgs[q].K, xw_cfgs[q].groups, lg);
         }
     }
 
@@ -953,6 +974,12 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         };
         auto warm_xw = [&](const XwConfig &xc) {
             if (!xc.ok()) return;
+            if (xc.wide) {
+                const Config c = {32, xc.K, 1, false};
+                warm_seqpair(false, c);
+                warm_seqpair(true, c);
+                return;
+            }
             w.profile = ctx->d_profile_xw.as<uint8_t>();
             w.xw_warps = (uint32_t)xc.W;
             w.xw_groups = (uint32_t)xc.groups;
@@ -1048,6 +1075,32 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         const XwConfig xc = xw_cfgs[q];
         uint32_t *xcnt = ctx->d_xw_counters.as<uint32_t>() + q * 4;
         int32_t *sc = score_row(q);
+        if (xc.wide) {
+            // one pass of 32 threads x K rows per pair (wavefront.cuh), its own profile, list and counters; then the
+            // 32-bit recomputation of what it listed, same shape
+            const Config c = {32, xc.K, 1, false};
+            cudaError_t e = launch_build_profile(ctx->d_queries.as<int8_t>() + ctx->q_off[q], ctx->q_len[q], ctx->d_submat.as<int8_t>(),
+                                                 32, xc.K, 1, ctx->d_profile_xw.as<uint8_t>(), st);
+            if (e != cudaSuccess) return e;
+            WfParams x = p;
+            x.scores = sc;
+            x.profile = ctx->d_profile_xw.as<uint8_t>();
+            x.passes = 1;
+            x.tile_first = fl;
+            x.tile_count = ctx->ntiles - fl;
+            x.task_counter = xcnt + 0;
+            x.resc_count = xcnt + 1;
+            x.resc_list = ctx->d_xw_list.as<uint32_t>();
+            xgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)xgrid, ((uint64_t)x.tile_count * kTilePairs + 15) / 16));
+            e = launch_wavefront(false, c, xgrid, st, x);
+            x.task_counter = xcnt + 2;
+            x.tile_first = 0;
+            x.tile_count = ctx->ntiles;
+            if (e == cudaSuccess) e = launch_wavefront(true, c, xgrid, st, x);
+            ctx->stats.launches += 3;
+            for (uint32_t t = fl; t < ctx->ntiles; ++t) padded += (uint64_t)32 * xc.K * (ctx->h_tile_cols[t] + 31) * kTileSeqs;
+            return e;
+        }
         cudaError_t e = launch_build_profile(ctx->d_queries.as<int8_t>() + ctx->q_off[q], ctx->q_len[q], ctx->d_submat.as<int8_t>(),
                                              32, xc.K, (uint32_t)xc.W, ctx->d_profile_xw.as<uint8_t>(), st);
         if (e == cudaSuccess)

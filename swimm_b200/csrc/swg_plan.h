@@ -25,6 +25,7 @@ struct XwConfig {        // how one query is mapped onto the long-sequence kerne
     int W = 0;           // warps (= concurrent passes of 32*K rows) per sequence pair; 0: the query does not fit (> 8192 rows)
     int groups = 0;      // sequence pairs a CTA works on at the same time (<= 16 / W): fewer groups = shorter steps
     double seconds = 0;  // estimated run time on `ctas` SMs
+    bool wide = false;   // instead: the 32-thread single-pass shape of the sequence-pair kernel (W = 1, queries <= 1024 rows)
     bool ok() const { return W > 0; }
 };
 

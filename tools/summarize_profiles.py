@@ -1,9 +1,9 @@
 """Summarise gpurun_out ncu output into profiles/ (launch-list shares, key metrics of the full captures)."""
 import csv, collections, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-G = os.path.join(ROOT, "gpurun_out")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+G = os.path.join(ROOT, "gpurun_out", sys.argv[2]) if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "r2p")
 P = os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
 # ---- launch list ----
 lines = [l for l in open(os.path.join(G, "launches.csv")) if not l.startswith("==")]
@@ -18,10 +18,11 @@ for row in csv.DictReader(lines):
     k = re.sub(r"\((?:int|bool)\)", "", k)
     fam = re.sub(r"wavefront_kernel<(Lane\d+), (\d+), (\d+), (\d), (\d), (\d+), (\d+)>", r"wavefront_kernel<\1,G=\2,K=*,MP=\4,GP=\5,imm=\6/\7>", k)
     fam = re.sub(r"wavefront_q2_kernel<(\d+), (\d+), (\d), (\d), (\d+), (\d+)>", r"wavefront_q2_kernel<G=\1,K=*,CIN=\3,COUT=\4,imm=\5/\6>", fam)
+    fam = re.sub(r"wavefront_xw_kernel<(Lane\d+), (\d+), (\d+), (\d+)>", r"wavefront_xw_kernel<\1,K=*,imm=\3/\4>", fam)
     tot[fam] += v; cnt[fam] += 1
 T = sum(tot.values())
 with open(os.path.join(P, tag + "_launch_list_summary.txt"), "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --scale 0.25 --steps 2 --warmup 3 --no-cpu-baseline --no-pipebench\n")
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --scale 0.25 --steps 2 --warmup 3 --no-cpu-baseline --no-pipebench --no-extra\n")
     f.write("(per-launch times are cold-cache and serialised: compare shares)\n\n%-64s %6s %12s %7s\n" % ("kernel", "n", "ms", "share"))
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         f.write("%-64s %6d %12.3f %6.2f%%\n" % (k[:64], cnt[k], v / 1e6, 100 * v / T))
@@ -39,7 +40,7 @@ keys = ["gpu__time_duration.sum", "sm__inst_executed_pipe_alu.avg.pct_of_peak_su
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
 res = {}
 keys += ["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
-for i, name in [(1, "q2_first_pass"), (2, "q2_middle_pass"), (3, "q2_last_pass"), (4, "seqpair_q144")]:
+for i, name in [(1, "q2_first_pass"), (2, "q2_middle_pass"), (3, "q2_last_pass"), (4, "seqpair_q144"), (5, "xw_cfg4_q5478")]:
     rep = os.path.join(G, "prof3_%d.ncu-rep" % i)
     if not os.path.exists(rep):
         continue
