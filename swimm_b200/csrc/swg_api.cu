@@ -106,6 +106,10 @@ struct swg_ctx {
     DeviceBuf d_scores, d_profile, d_profile32, d_boundary, d_counters, d_resc_list, d_topk_scratch, d_top_out;
     DeviceBuf d_profile_q2, d_lines, d_resc_list2, d_q2_counters;
     DeviceBuf d_profile_xw, d_xw_counters, d_xw_list;
+    DeviceBuf d_vt;                          // column-chunk tables of the long tiles (uint4 per chunk), all queries of a run
+    uint4 *h_vt = nullptr;                   // pinned staging of the same
+    size_t h_vt_cap = 0;
+    int submat_max = 0;                      // largest entry of the current substitution matrix
     DeviceBuf d_q_off, d_align_lines, d_coords;                      // coordinate pass (align_ends.cu)     // long-sequence kernel (wavefront_xw.cuh)
     std::vector<WorkItem> items;            // schedule of the last run
     std::vector<cudaEvent_t> item_events;   // items.size() + 1 marks
@@ -122,6 +126,7 @@ struct swg_ctx {
     // options
     long long_cols = kDefaultLongCols;
     long xw_warps = 0, xw_rows = 0;         // forced shape of the long-sequence kernel (0: planner)
+    long chunk_columns = 0;                 // column chunks of long tiles for one-pass queries: 0 planner, 1 off, > 1 this many columns
     long long_kernel = 1;                   // 1: long tiles run the cross-warp wavefront kernel (K3), 0: the 32-thread shape of K1
     long force_group = 0, force_rows = 0;
     long query_pairing = 1;                 // 0: never pair queries, 1: pair when the planner expects a gain, 2: always
@@ -385,6 +390,8 @@ void swg_gpu_destroy(swg_ctx *ctx)
     ctx->d_profile_xw.release();
     ctx->d_xw_counters.release();
     ctx->d_xw_list.release();
+    ctx->d_vt.release();
+    if (ctx->h_vt) cudaFreeHost(ctx->h_vt);
     ctx->d_q_off.release();
     ctx->d_align_lines.release();
     ctx->d_coords.release();
@@ -419,6 +426,9 @@ int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value)
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
             return fail(ctx, SWG_ERR_ARG, "xw_warps must be 0, 1, 2, 4, 8 or 16");
         ctx->xw_warps = value;
+    } else if (!strcmp(name, "chunk_columns")) {
+        if (value < 0) return fail(ctx, SWG_ERR_ARG, "chunk_columns must be 0 (planner), 1 (off) or a column count");
+        ctx->chunk_columns = value;
     } else if (!strcmp(name, "xw_rows")) {
         if (value < 0 || value > kMaxRowsPerThread) return fail(ctx, SWG_ERR_ARG, "xw_rows must be 0..32");
         ctx->xw_rows = value;
@@ -709,6 +719,8 @@ int swg_gpu_set_queries(swg_ctx *ctx, const signed char *queries, const uint16_t
     }
     ctx->open_gap = open_gap;
     ctx->extend_gap = extend_gap;
+    ctx->submat_max = 0;
+    for (int i = 0; i < 768; ++i) ctx->submat_max = std::max(ctx->submat_max, (int)submat[i]);
     ctx->queries_ready = true;
     ctx->run_done = false;
     ctx->stats.h2d_bytes = total + 768;
@@ -821,6 +833,8 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     std::vector<uint32_t> item_first_long(items.size(), ctx->ntiles);
     std::vector<int> item_long_grid(items.size(), 0);
     std::vector<XwConfig> xw_cfgs(nq);
+    std::vector<uint4> vt_all;                          // column-chunk tables, query after query
+    std::vector<std::pair<size_t, size_t>> vt_of(nq, std::make_pair((size_t)0, (size_t)0));   // (offset, count) in vt_all
     bool any_xw = false;
     if (ctx->ntiles) {
         const double res = (double)ctx->local_residues, res9 = res * 1e-9;
@@ -876,16 +890,52 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 XwConfig xc = choose_xw_config(m, pairs, long_cols * kTilePairs, (double)ctx->maxcols, lg, ctx->xw_warps, ctx->xw_rows);
                 if (m <= (uint32_t)kMaxPassRows && !ctx->xw_warps && !ctx->xw_rows) {
                     const int K = (int)((m + 31) / 32);
-                    const double active = std::min(16.0, std::max(1.0, pairs / lg));
+                    // Column chunks.  An alignment with a positive score has fewer than m * Smax / ge database-only
+                    // columns (each costs at least ge, the matches earn at most m * Smax), so it spans at most
+                    // B = m + m * Smax / ge columns: chunks of C columns that overlap by B each contain every
+                    // alignment that starts in their first C - B columns, and a sequence's score is the best of its
+                    // chunks -- exactly.  For a short query B is far below a long sequence's length, and the chunks are
+                    // independent tasks: no serial chain is left.
+                    size_t n_chunks = 0;
+                    uint32_t C = 0, stride = 0;
+                    if (ctx->extend_gap >= 1 && ctx->submat_max >= 1 && ctx->chunk_columns != 1) {
+                        const uint64_t B = (uint64_t)m + (uint64_t)m * ctx->submat_max / ctx->extend_gap + 1;
+                        const uint64_t want = ctx->chunk_columns > 1 ? (uint64_t)ctx->chunk_columns : std::max<uint64_t>(2 * B, 2048);
+                        C = (uint32_t)std::min<uint64_t>((std::max(want, B + 8) + 7) / 8 * 8, 1u << 20);
+                        stride = (uint32_t)((C - B) / 8 * 8);
+                        if (stride >= 8 && (uint64_t)C * 2 <= ctx->maxcols) {
+                            const size_t first = vt_all.size();
+                            for (uint32_t t = ctx->ntiles; t-- > fl;) {
+                                const uint32_t cols = ctx->h_tile_cols[t];
+                                if (cols <= C) { vt_all.push_back(make_uint4(t, 0, cols, 0)); continue; }
+                                for (uint32_t c0 = 0;; c0 += stride) {
+                                    const uint32_t len = std::min(C, cols - c0);
+                                    vt_all.push_back(make_uint4(t, c0, len, 0));
+                                    if (c0 + len >= cols) break;
+                                }
+                            }
+                            std::stable_sort(vt_all.begin() + first, vt_all.end(), [](const uint4 &a, const uint4 &b) { return a.z > b.z; });
+                            n_chunks = vt_all.size() - first;
+                            vt_of[q] = std::make_pair(first, n_chunks);
+                        }
+                    }
+                    double chunk_cols = 0.0;
+                    for (size_t k = 0; k < n_chunks; ++k) chunk_cols += vt_all[vt_of[q].first + k].z;
+                    const double work_cols = n_chunks ? chunk_cols : long_cols;
+                    const double longest = n_chunks ? (double)C : (double)ctx->maxcols;
+                    const double active = std::min(16.0, std::max(1.0, (n_chunks ? (double)n_chunks : (double)(ctx->ntiles - fl)) * kTilePairs / lg));
                     const double step = std::max(step_seconds_alone(K), step_seconds_loaded(K, shape_rate(32, K, 1)) * active / 16.0);
-                    const double t_wide = std::max(long_cols * kTilePairs / (lg * 16.0), (double)ctx->maxcols) * step;
-                    if (!xc.ok() || t_wide < xc.seconds) {
+                    const double t_wide = std::max(work_cols * kTilePairs / (lg * 16.0), longest) * step;
+                    // (the long-sequence kernel's hand-off makes its steps slower than this model says: it must win clearly)
+                    if (!xc.ok() || n_chunks || t_wide < 1.4 * xc.seconds) {
                         xc = XwConfig();
                         xc.K = K;
                         xc.W = 1;
                         xc.groups = 16;
                         xc.wide = true;
                         xc.seconds = t_wide;
+                    } else {
+                        vt_of[q] = std::make_pair((size_t)0, (size_t)0);
                     }
                 }
                 xw_cfgs[q] = xc;
@@ -909,7 +959,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                         ii, fl, limit, t_keep * 1e3, t_split * 1e3, t_long * 1e3, lg);
             }
             if (!all_ok) {                     // (a forced shape too small for the query, or nothing to gain)
-                for (uint32_t q : qs) xw_cfgs[q] = XwConfig();
+                for (uint32_t q : qs) { xw_cfgs[q] = XwConfig(); vt_of[q] = std::make_pair((size_t)0, (size_t)0); }
                 if (!it.pair && forced) item_first_long[ii] = fl;      // forced threshold: the 32-thread shape
                 continue;
             }
@@ -918,10 +968,10 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             any_xw = true;
             if (ctx->verbose)
                 for (uint32_t q : qs)
-                    fprintf(stderr, "[swg] query %u (%u rows): tiles %u..%u (%.0f columns x 16) on %s, %d warps x %d rows, %d pairs per CTA, %d CTAs\n",
+                    fprintf(stderr, "[swg] query %u (%u rows): tiles %u..%u (%.0f columns x 16) on %s, %d warps x %d rows, %d pairs per CTA, %d CTAs, %zu column chunks\n",
                             q, (unsigned)ctx->q_len[q], fl, ctx->ntiles - 1, long_cols,
                             xw_cfgs[q].wide ? "the 32-thread shape of the sequence-pair kernel" : "the long-sequence kernel", xw_cfgs[q].W,
-                            xw_cfgs[q].K, xw_cfgs[q].groups, lg);
+                            xw_cfgs[q].K, xw_cfgs[q].groups, lg, vt_of[q].second);
         }
     }
 
@@ -936,6 +986,20 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         SWG_CUDA(ctx, ctx->d_profile_q2.reserve((size_t)kQ2ProfileBytes));
         SWG_CUDA(ctx, ctx->d_resc_list2.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
         SWG_CUDA(ctx, ctx->d_q2_counters.reserve((size_t)q2_launches * sizeof(uint32_t)));
+    }
+    if (!vt_all.empty()) {
+        const size_t bytes = vt_all.size() * sizeof(uint4);
+        if (bytes > ctx->h_vt_cap) {
+            if (ctx->h_vt) cudaFreeHost(ctx->h_vt);
+            ctx->h_vt = nullptr;
+            ctx->h_vt_cap = 0;
+            SWG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_vt, 2 * bytes));
+            ctx->h_vt_cap = 2 * bytes;
+        }
+        SWG_CUDA(ctx, ctx->d_vt.reserve(bytes));
+        SWG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // a previous run may still read the tables
+        memcpy(ctx->h_vt, vt_all.data(), bytes);
+        SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_vt.p, ctx->h_vt, bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (any_xw) {
         SWG_CUDA(ctx, ctx->d_profile_xw.reserve((size_t)16 * kPassBytes));
@@ -1091,8 +1155,19 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             x.task_counter = xcnt + 0;
             x.resc_count = xcnt + 1;
             x.resc_list = ctx->d_xw_list.as<uint32_t>();
-            xgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)xgrid, ((uint64_t)x.tile_count * kTilePairs + 15) / 16));
+            uint64_t tasks = (uint64_t)x.tile_count * kTilePairs;
+            if (vt_of[q].second) {
+                // column chunks instead of whole tiles: scores merged with atomicMax, hence zeroed first
+                x.vt = ctx->d_vt.as<uint4>() + vt_of[q].first;
+                x.vt_count = (uint32_t)vt_of[q].second;
+                tasks = (uint64_t)x.vt_count * kTilePairs;
+                e = cudaMemsetAsync(sc + (size_t)fl * kTileSeqs, 0, (size_t)(ctx->ntiles - fl) * kTileSeqs * sizeof(int32_t), st);
+                if (e != cudaSuccess) return e;
+            }
+            xgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)xgrid, (tasks + 15) / 16));
             e = launch_wavefront(false, c, xgrid, st, x);
+            x.vt = nullptr;
+            x.vt_count = 0;
             x.task_counter = xcnt + 2;
             x.tile_first = 0;
             x.tile_count = ctx->ntiles;

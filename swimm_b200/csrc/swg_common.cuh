@@ -78,6 +78,10 @@ struct WfParams {
     // the two 16-bit lanes are independent streams of queries: a lane may start a new query in a launch in which
     // the other lane continues one
     uint32_t lane_flags;          // kLaneActive / kLaneFirst bits, low lane in bits 0-1, high lane in bits 2-3
+    // column chunks of long tiles (sequence-pair kernel, short queries): when vt != NULL the launch's tasks are the
+    // entries {tile, first column, columns, 0} of this table instead of whole tiles, and scores are merged with atomicMax
+    const uint4 *vt;
+    uint32_t vt_count;
     // long-sequence kernel (wavefront_xw.cuh) only
     uint32_t xw_warps;            // W: warps (= concurrent passes) per sequence pair, 1, 2, 4, 8 or 16
     uint32_t xw_groups;           // sequence pairs a CTA works on at the same time (<= 16 / W)

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
     const uint32_t pad_pk = (L::kSeqs == 2) ? 0x60006000u : 0x00006000u;
 
     uint32_t ntasks;
-    if (L::kSeqs == 2) ntasks = p.tile_count * TPT;
+    if (L::kSeqs == 2) ntasks = (p.vt ? p.vt_count : p.tile_count) * TPT;
     else ntasks = *p.resc_count;
 
     auto fetch_task = [&]() -> uint32_t {
@@ -199,6 +199,19 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
             if (L::kSeqs == 2) {
                 const uint32_t bb = (uint32_t)b;
                 const int s_lo = (int)(short)(bb & 0xffffu), s_hi = (int)(short)(bb >> 16);
+                if (p.vt) {
+                    // a column chunk of a long sequence: the sequence's score is the best of its chunks; the chunk
+                    // that first lifts it to kOverflow16 lists it
+                    if (global_seq_index(p, lseq) < p.n_total) {
+                        const int old = atomicMax(p.scores + lseq, s_lo);
+                        if (s_lo >= kOverflow16 && old < kOverflow16) p.resc_list[atomicAdd(p.resc_count, 1u)] = lseq;
+                    }
+                    if (global_seq_index(p, lseq + 1) < p.n_total) {
+                        const int old = atomicMax(p.scores + lseq + 1, s_hi);
+                        if (s_hi >= kOverflow16 && old < kOverflow16) p.resc_list[atomicAdd(p.resc_count, 1u)] = lseq + 1;
+                    }
+                    return;
+                }
                 if (global_seq_index(p, lseq) < p.n_total) {
                     p.scores[lseq] = s_lo;
                     if (s_lo >= kOverflow16) p.resc_list[atomicAdd(p.resc_count, 1u)] = lseq;
@@ -228,19 +241,27 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
         uint32_t half = 0, lseq = 0, ncols = 0;
         const uint2 *words = nullptr;
         if (have) {
-            uint32_t tile, pair;
+            uint32_t tile, pair, col0 = 0;
             if (L::kSeqs == 2) {
-                tile = p.tile_first + p.tile_count - 1 - task / TPT;        // longest tiles first
                 pair = (task % TPT) * GPW + g;
+                if (p.vt) {
+                    const uint4 v = p.vt[task / TPT];                        // a column chunk of a long tile
+                    tile = v.x;
+                    col0 = v.y;
+                    ncols = v.z;
+                } else {
+                    tile = p.tile_first + p.tile_count - 1 - task / TPT;    // longest tiles first
+                    ncols = p.tile_cols[tile];
+                }
                 lseq = tile * kTileSeqs + 2 * pair;
             } else {
                 lseq = p.resc_list[task];
                 tile = lseq / kTileSeqs;
                 pair = (lseq % kTileSeqs) >> 1;
                 half = lseq & 1u;
+                ncols = p.tile_cols[tile];
             }
-            ncols = p.tile_cols[tile];
-            words = reinterpret_cast<const uint2 *>(p.db + p.tile_off[tile] + pair);
+            words = reinterpret_cast<const uint2 *>(p.db + p.tile_off[tile] + (size_t)(col0 / kChunkCols) * kTilePairs + pair);
         }
         const uint32_t data_trips = ncols / NC;
         const uint32_t trips = data_trips < kMinTrips ? kMinTrips : data_trips;

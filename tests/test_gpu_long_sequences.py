@@ -125,3 +125,45 @@ def test_long_kernel_off_matches(gpu, oracle):
         got, _ = _with(gpu, {"long_kernel": lk, "long_threshold": 1000, "query_pairing": 0},
                        lambda: gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 0, want_scores=True))
         assert np.array_equal(got, want), (lk, np.argwhere(got != want)[:8])
+
+
+def _gappy_copy(rng, frag, p_ins=0.04, p_del=0.03, p_sub=0.08):
+    """A homolog of `frag` with insertions, deletions and substitutions (alignments with gaps span more columns)."""
+    out = []
+    for c in frag:
+        if rng.random() < p_del:
+            continue
+        out.append(c if rng.random() >= p_sub else synth.random_residues(rng, 1)[0])
+        while rng.random() < p_ins:
+            out.extend(synth.random_residues(rng, int(rng.integers(1, 12))))
+    return np.array(out, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("chunk", [0, 1, 1200, 4096])
+@pytest.mark.parametrize("matrix,go,ge", [("blosum62", 10, 2), ("blosum62", 11, 1), ("pam250", 5, 1)])
+def test_short_queries_column_chunks_of_long_sequences(gpu, oracle, chunk, matrix, go, ge):
+    """One-pass queries against long sequences: the long tiles are cut into overlapping column chunks (overlap = the
+    longest span an alignment of the query can have), searched as independent tasks, and merged with max -- exact.
+    Gappy homologs planted across chunk boundaries; chunk length by the planner (0), off (1) and forced."""
+    rng = np.random.default_rng(31 + chunk + ge)
+    q = synth.make_queries(rng, [25, 60, 144])
+    lens = np.concatenate([rng.integers(30, 400, 600), rng.integers(6000, 30000, 24)])
+    db = synth.make_seqset(rng, lens)
+    for t in range(600, 624):                      # homologs at many offsets of every long sequence
+        s0, L = int(db.offsets[t]), int(lens[t])
+        for pos in range(150, L - 700, 997):
+            qi = int(rng.integers(q.n))
+            frag = _gappy_copy(rng, q.seq(qi))
+            db.residues[s0 + pos:s0 + pos + len(frag)] = frag[:max(0, L - pos)][:len(frag)]
+    _, dl, dc = synth.length_sorted(db)
+    _, ql, qc = synth.length_sorted(q)
+    do = np.zeros(db.n + 1, np.uint64)
+    np.cumsum(dl.astype(np.uint64), out=do[1:])
+    qo = np.zeros(q.n + 1, np.uint32)
+    np.cumsum(ql.astype(np.uint32), out=qo[1:])
+    want = oracle.search(qc, qo, dc, do, host.submat(matrix), go, ge)
+    gpu.load_db(dl, dc)
+    for pairing in (0, 1):
+        got, _ = _with(gpu, {"long_threshold": 2000, "chunk_columns": chunk, "query_pairing": pairing},
+                       lambda: gpu.search(qc, ql, qo[:-1], host.submat(matrix), go, ge, 0, want_scores=True))
+        assert np.array_equal(got, want), (pairing, np.argwhere(got != want)[:8])

@@ -13,7 +13,7 @@ s = gpu.GpuSearch(0)
 
 
 def run(tag, w, opts, reps=5, verbose=False):
-    for k, v in {"long_threshold": 0, "query_pairing": 1, "long_kernel": 1, "xw_warps": 0, "xw_rows": 0, "verbose": 0}.items():
+    for k, v in {"long_threshold": 0, "query_pairing": 1, "long_kernel": 1, "xw_warps": 0, "xw_rows": 0, "verbose": 0, "chunk_columns": 0}.items():
         s.set_option(k, v)
     for k, v in opts.items():
         s.set_option(k, v)
@@ -39,14 +39,16 @@ class W1:      # cfg1 with the FASTA-order generator of round 1 (longest sequenc
         self.qo = np.zeros(2, np.uint32); self.qo[1] = 144
 
 
-for name, w in [("cfg1/r1", W1()), ("cfg1", bench.Workload("cfg1")), ("cfg5", bench.Workload("cfg5")), ("cfg4", bench.Workload("cfg4"))]:
+for name, w in [("cfg1", bench.Workload("cfg1")), ("cfg5", bench.Workload("cfg5")), ("cfg4", bench.Workload("cfg4"))]:
     s.load_db(w.dl, w.dc)
     print(name, "longest", w.dl[-3:], "residues", len(w.dc), flush=True)
     run(name + " auto", w, {}, verbose=True)
     run(name + " no split", w, {"long_threshold": 65535})
     run(name + " old long kernel", w, {"long_kernel": 0})
-    for thr in (1024, 2048, 4096):
+    run(name + " no column chunks", w, {"chunk_columns": 1})
+    for c in (1024, 1536, 3072, 4096):
         if name.startswith("cfg1"):
-            run(name + " xw > %d" % thr, w, {"long_threshold": thr})
-            run(name + " xw W4 K2 > %d" % thr, w, {"long_threshold": thr, "xw_warps": 4, "xw_rows": 2})
-            run(name + " old > %d" % thr, w, {"long_threshold": thr, "long_kernel": 0})
+            run(name + " chunks of %d" % c, w, {"chunk_columns": c})
+    for thr in (1024, 2048):
+        if name.startswith("cfg1"):
+            run(name + " long > %d" % thr, w, {"long_threshold": thr})
