@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <set>
+#include <string>
 #include <vector>
 
 #include "../../include/swimm_gpu.h"
@@ -126,6 +127,9 @@ struct swg_ctx {
     // options
     long long_cols = kDefaultLongCols;
     long xw_warps = 0, xw_rows = 0;         // forced shape of the long-sequence kernel (0: planner)
+    long trace = 0;                         // 1: an event after every launch of a run, timeline printed by swg_gpu_sync
+    std::vector<std::pair<std::string, cudaEvent_t>> trace_marks;
+    std::vector<cudaEvent_t> trace_pool;
     long chunk_columns = 0;                 // column chunks of long tiles for one-pass queries: 0 planner, 1 off, > 1 this many columns
     long long_kernel = 1;                   // 1: long tiles run the cross-warp wavefront kernel (K3), 0: the 32-thread shape of K1
     long force_group = 0, force_rows = 0;
@@ -398,6 +402,7 @@ void swg_gpu_destroy(swg_ctx *ctx)
     for (cudaEvent_t ev : ctx->q_events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->item_events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->trace_pool) cudaEventDestroy(ev);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -426,6 +431,8 @@ int swg_gpu_set_option(swg_ctx *ctx, const char *name, long value)
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
             return fail(ctx, SWG_ERR_ARG, "xw_warps must be 0, 1, 2, 4, 8 or 16");
         ctx->xw_warps = value;
+    } else if (!strcmp(name, "trace")) {
+        ctx->trace = value;
     } else if (!strcmp(name, "chunk_columns")) {
         if (value < 0) return fail(ctx, SWG_ERR_ARG, "chunk_columns must be 0 (planner), 1 (off) or a column count");
         ctx->chunk_columns = value;
@@ -1073,6 +1080,18 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     }
 
     SWG_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+    ctx->trace_marks.clear();
+    auto mark = [&](const char *label, cudaStream_t st) {
+        if (!ctx->trace) return;
+        if (ctx->trace_marks.size() >= ctx->trace_pool.size()) {
+            cudaEvent_t ev;
+            if (cudaEventCreate(&ev) != cudaSuccess) return;
+            ctx->trace_pool.push_back(ev);
+        }
+        cudaEvent_t ev = ctx->trace_pool[ctx->trace_marks.size()];
+        cudaEventRecord(ev, st);
+        ctx->trace_marks.push_back(std::make_pair(std::string(label), ev));
+    };
     SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t), ctx->stream));
     SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_xw_counters.p, 0, std::max<uint64_t>(nq, 1) * 4 * sizeof(uint32_t), ctx->stream));
     if (q2_launches) SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_q2_counters.p, 0, (size_t)q2_launches * sizeof(uint32_t), ctx->stream));
@@ -1130,7 +1149,9 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         r.resc_count = cnt + 3;
         r.resc_list = list;
         ctx->stats.launches += 1;
-        return launch_wavefront(true, wide_cfg, grid, st, r);
+        e = launch_wavefront(true, wide_cfg, grid, st, r);
+        mark("32-bit recomputation", st);
+        return e;
     };
 
     // Long tiles [fl, ntiles) of query q on the long-sequence kernel (K3): profile of all W passes, the 16-bit launch
@@ -1171,7 +1192,9 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             x.task_counter = xcnt + 2;
             x.tile_first = 0;
             x.tile_count = ctx->ntiles;
+            mark("long tiles: 32-thread shape", st);
             if (e == cudaSuccess) e = launch_wavefront(true, c, xgrid, st, x);
+            mark("long tiles: 32-bit recomputation", st);
             ctx->stats.launches += 3;
             for (uint32_t t = fl; t < ctx->ntiles; ++t) padded += (uint64_t)32 * xc.K * (ctx->h_tile_cols[t] + 31) * kTileSeqs;
             return e;
@@ -1195,8 +1218,10 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         // no more CTAs than there are pairs to keep their groups busy
         xgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)xgrid, ((uint64_t)x.tile_count * kTilePairs + xc.groups - 1) / xc.groups));
         e = launch_xw_l16(xc.K, xgrid, st, x);
+        mark("long tiles: long-sequence kernel", st);
         x.task_counter = xcnt + 2;
         if (e == cudaSuccess) e = launch_xw_l32(xc.K, xgrid, st, x);
+        mark("long tiles: 32-bit recomputation", st);
         ctx->stats.launches += 3;
         ctx->stats.cells += 0;
         for (uint32_t t = fl; t < ctx->ntiles; ++t)
@@ -1297,7 +1322,9 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 if (e != cudaSuccess) break;
                 pq.profile = ctx->d_profile_q2.as<uint8_t>();
                 pq.task_counter = ctx->d_q2_counters.as<uint32_t>() + q2_next_counter++;
+                mark("query-pair profile", ks);
                 e = launch_q2(L.G, L.K, cin, cout, grid, ks, pq);
+                mark("query-pair kernel", ks);
                 ctx->stats.launches += 1;
                 ctx->stats.pair_launches += 1;
                 ctx->stats.stream_bytes += ctx->db_units * sizeof(uint4) + ((int)cin + (int)cout) * ctx->line_units * sizeof(uint2);
@@ -1377,11 +1404,14 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             p.tile_first = 0;
             p.tile_count = main_tiles;
             p.task_counter = cnt + 1;
+            mark("before the sequence-pair kernel", forked ? ctx->side_stream : ctx->stream);
             e = launch_wavefront(false, main_cfg, grid, forked ? ctx->side_stream : ctx->stream, p);
+            mark("sequence-pair kernel", forked ? ctx->side_stream : ctx->stream);
             if (e == cudaSuccess && forked) e = cudaEventRecord(ctx->ev_join, ctx->side_stream);
             ctx->stats.launches += 1;
         }
         if (e == cudaSuccess && forked) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+        mark("joined", ctx->stream);
         if (e == cudaSuccess) e = recompute32(q, ctx->d_resc_list.as<uint32_t>(), false, ctx->stream);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "search kernel launch");
         SWG_CUDA(ctx, cudaEventRecord(ctx->item_events[ii + 1], ctx->stream));
@@ -1412,6 +1442,12 @@ int swg_gpu_sync(swg_ctx *ctx)
             SWG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->chunk_events[2 * c], ctx->chunk_events[2 * c + 1]));
             ms_topr += ms;
         }
+        if (ctx->trace)
+            for (const auto &mk : ctx->trace_marks) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, ctx->ev_begin, mk.second) == cudaSuccess)
+                    fprintf(stderr, "[swg trace] %9.3f ms  %s\n", ms, mk.first.c_str());
+            }
         ctx->stats.device_seconds = ms_all * 1e-3;
         ctx->stats.search_seconds = (ms_all - ms_topr) * 1e-3;
         ctx->stats.topr_seconds = ms_topr * 1e-3;

@@ -235,7 +235,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
         const uint32_t task = next_task;
         const bool have = task < ntasks;
         if (!have && !pending) break;
-        if (have) next_task = fetch_task();          // fetched one task ahead: the atomic's latency is hidden
+        // The next task is drawn 16 trips (64 columns: far more than the atomic's latency) before this one ends, during
+        // its last pass -- not at its start: a warp that reserves its next task while it begins a long one commits to
+        // two long tasks in a row, which breaks the longest-first balance when there are only a few tasks per warp.
 
         // ---- decode the task (a flush segment of padding columns when there is none left) ----
         uint32_t half = 0, lseq = 0, ncols = 0;
@@ -322,8 +324,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
             for (uint32_t trip = 0; trip < FI; ++trip) trip_body(head_steps, trip);
             if (pending && pass == 0) { finalize(pend_lseq); pending = false; }
             store_on = MP && t == G - 1 && (pass + 1 < seg_passes);
+            const uint32_t fetch_trip = (have && pass + 1 == seg_passes) ? (trips > FI + 16 ? trips - 16 : FI) : 0xffffffffu;
 #pragma unroll 1
-            for (uint32_t trip = FI; trip < trips; ++trip) trip_body(steady_steps, trip);
+            for (uint32_t trip = FI; trip < trips; ++trip) {
+                if (trip == fetch_trip) next_task = fetch_task();
+                trip_body(steady_steps, trip);
+            }
             if (MP) hf_in = ring[0];          // enters the segment's last column, processed in the next segment's step 0
         }
         if (have) { pending = true; pend_lseq = lseq; }

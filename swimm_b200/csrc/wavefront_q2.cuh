@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
         const uint32_t task = next_task;
         const bool have = task < ntasks;
         if (!have && !pending) break;
-        if (have) next_task = fetch_task();
+        // (the next task is drawn 16 trips before this one ends, not at its start: see wavefront.cuh)
 
         uint32_t half = 0, lseq = 0, ncols = 0;
         const uint2 *words = nullptr;
@@ -243,8 +243,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
 #pragma unroll 1
         for (uint32_t trip = 0; trip < FI; ++trip) trip_body(head_steps, trip);
         if (pending) { finalize(pend_lseq); pending = false; }
+        const uint32_t fetch_trip = have ? (trips > FI + 16 ? trips - 16 : FI) : 0xffffffffu;
 #pragma unroll 1
-        for (uint32_t trip = FI; trip < trips; ++trip) trip_body(steady_steps, trip);
+        for (uint32_t trip = FI; trip < trips; ++trip) {
+            if (trip == fetch_trip) next_task = fetch_task();
+            trip_body(steady_steps, trip);
+        }
         if (CIN) hf_in = ring[0];
         st_cur += seg_cols;                                       // the next segment's head steps continue this line
         if (have) { pending = true; pend_lseq = lseq; }
