@@ -90,6 +90,35 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def sm_clock_mhz(index):
+    """Current SM clock of one GPU (NVML); None when NVML is not usable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        return float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+    except Exception:
+        return None
+
+
+def timed_steps(s, step, steps, warm, min_warm_seconds=0.4):
+    """`warm` untimed steps -- and as many more as it takes to keep the GPU busy for min_warm_seconds, so that a
+    millisecond-sized workload is not timed while the SM clock is still ramping up from idle -- then `steps` timed steps.
+    Returns the per-step device seconds (CUDA events of the library)."""
+    t0 = time.time()
+    n = 0
+    while n < warm or time.time() - t0 < min_warm_seconds:
+        step()
+        n += 1
+        if n >= 5000:
+            break
+    per = []
+    for _ in range(steps):
+        step()
+        per.append(s.stats()["device_seconds"])
+    return per, n
+
+
 def physical_device_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -401,18 +430,15 @@ def main():
             l2, c2, _ = w2.shard(rank, world)
             s.load_db_shard(l2, c2, rank, world, w2.n_total)
             s.set_queries(w2.qc, w2.ql, w2.qo[:-1], b62, GO, GE)
-            for _ in range(warm_):
-                step_resident()
             barrier()
-            s.sync()
-            d2 = 0.0
-            for _ in range(steps_):
-                step_resident()
-                d2 += s.stats()["device_seconds"]
+            per_step, warmed = timed_steps(s, step_resident, steps_, warm_)
+            mhz = sm_clock_mhz(physical_device_index(local_rank))
             barrier()
-            d2 = max_over_ranks(d2)
-            strong[name] = {"workload": w2.describe(), "n_gpus": world, "steps": steps_, "warmup": warm_,
+            d2 = max_over_ranks(sum(per_step))
+            log("[rank %d] strong %s per-step ms: %s" % (rank, name, " ".join("%.3f" % (x * 1e3) for x in per_step)))
+            strong[name] = {"workload": w2.describe(), "n_gpus": world, "steps": steps_, "warmup": warmed,
                             "ms_per_step": d2 / steps_ * 1e3, "gcups": w2.cells * steps_ / d2 / 1e9,
+                            "ms_per_step_min_this_rank": min(per_step) * 1e3, "sm_mhz_after": mhz,
                             "note": "fixed total database split over the ranks by tiles; efficiency = gcups / (N x the N=1 line's gcups)"}
             log("[rank %d] strong %s: %.3f ms/step" % (rank, name, d2 / steps_ * 1e3))
             del w2, l2, c2
@@ -548,13 +574,14 @@ def other_configs(s, gpu, peaks):
             s.load_db(loaded.dl, loaded.dc)
         w = loaded
         s.set_queries(w.qc, w.ql, w.qo[:-1], host.submat(matrix), go, ge)
-        for _ in range(warm):
+
+        def one():
             s.run(TOP)
             s.sync()
+        timed_steps(s, one, 0, warm)
         dev, qs = 0.0, np.zeros(w.q.n)
         for _ in range(steps):
-            s.run(TOP)
-            s.sync()
+            one()
             dev += s.stats()["device_seconds"]
             qs += s.query_seconds()
         kinds = s.query_kernels()
@@ -562,6 +589,7 @@ def other_configs(s, gpu, peaks):
         kind = 1 if share1 >= 0.5 else 0
         gc = w.cells * steps / dev / 1e9
         rec = {"workload": w.describe() + ", %s, gap %d/%d" % (matrix, go, ge), "gcups": gc, "ms_per_step": dev / steps * 1e3,
+               "sm_mhz_after": sm_clock_mhz(0),
                "dominant_kernel": KERNELS[kind][1], "share_of_search_time": share1 if kind else 1.0 - share1}
         if peaks:
             fast = (go + ge, ge) == (12, 2)
