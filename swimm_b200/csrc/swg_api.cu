@@ -755,13 +755,9 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     const int grid = ctx->grid_blocks > 0 ? (int)std::min<long>(ctx->grid_blocks, ctx->sm_count) : ctx->sm_count;
     const int warps_per_block = kBlockThreads / 32;
     const size_t warps = (size_t)grid * warps_per_block;
-    // the pass lines of multi-launch groups take 8 bytes per database column: only when that fits comfortably
+    // the pass lines of multi-launch groups take 8 bytes per database column: only when that fits comfortably (the
+    // driver is asked for free memory only when a plan needs lines that are not allocated yet, see below)
     bool lines_fit = ctx->pass_lines != 0;
-    if (lines_fit && ctx->d_lines.cap < (ctx->line_units + warps * 4 * (uint64_t)(kQ2MinSegCols + kQ2LineSlack) + 2) * sizeof(uint2)) {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
-        lines_fit = (double)ctx->line_units * sizeof(uint2) < 0.6 * (double)free_b;
-    }
     // ---- score rows: a window of queries ----
     // All nq rows when the caller wants the full score vectors.  Otherwise at most `score_budget` bytes of rows: the
     // batch is searched in chunks of that many queries, each chunk followed by its own top-r selection, so that a
@@ -822,7 +818,16 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 if (it.launches.size() > 1) q2_lines = true;
             }
         if (!q2_lines) break;
-        const cudaError_t le = ctx->d_lines.reserve((ctx->line_units + dummy_lines + 2) * sizeof(uint2));
+        const size_t line_bytes = (ctx->line_units + dummy_lines + 2) * sizeof(uint2);
+        if (ctx->d_lines.cap < line_bytes && attempt == 0) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+            if ((double)ctx->line_units * sizeof(uint2) >= 0.6 * (double)free_b) {
+                shape.lines_fit = false;           // plan again without multi-launch groups
+                continue;
+            }
+        }
+        const cudaError_t le = ctx->d_lines.reserve(line_bytes);
         if (le == cudaSuccess) break;
         if (le != cudaErrorMemoryAllocation || attempt == 1) return cuda_fail(ctx, le, "pass lines");
         cudaGetLastError();              // not enough memory for the pass lines after all: plan again without them
@@ -1156,17 +1161,28 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
 
     // Long tiles [fl, ntiles) of query q on the long-sequence kernel (K3): profile of all W passes, the 16-bit launch
     // (scores merged with atomicMax, hence zeroed first), and the 32-bit recomputation of what it listed, same shape.
-    auto enqueue_xw = [&](uint64_t q, uint32_t fl, int xgrid, cudaStream_t st) -> cudaError_t {
+    // `phase` 0: only what precedes the search launch (profile build, zeroing); 1: only the launches; 2: both.  The
+    // caller forks the side stream BETWEEN the two phases: the long tiles' launch and the main launch then become
+    // ready at the same moment and the high-priority stream wins the SMs it needs.  (When the main kernel, whose CTAs
+    // are persistent, got all SMs first, the long tiles waited for the whole main kernel: a 0.9 ms search took 1.9.)
+    int long_ctas = 0;                                  // CTAs of the last long-tile launch
+    auto enqueue_xw = [&](uint64_t q, uint32_t fl, int xgrid, cudaStream_t st, int phase) -> cudaError_t {
         const XwConfig xc = xw_cfgs[q];
         uint32_t *xcnt = ctx->d_xw_counters.as<uint32_t>() + q * 4;
         int32_t *sc = score_row(q);
+        const bool zero_first = !xc.wide || vt_of[q].second != 0;       // scores merged with atomicMax
+        if (phase != 1) {
+            cudaError_t e = launch_build_profile(ctx->d_queries.as<int8_t>() + ctx->q_off[q], ctx->q_len[q], ctx->d_submat.as<int8_t>(),
+                                                 32, xc.K, xc.wide ? 1u : (uint32_t)xc.W, ctx->d_profile_xw.as<uint8_t>(), st);
+            if (e == cudaSuccess && zero_first)
+                e = cudaMemsetAsync(sc + (size_t)fl * kTileSeqs, 0, (size_t)(ctx->ntiles - fl) * kTileSeqs * sizeof(int32_t), st);
+            if (e != cudaSuccess || phase == 0) return e;
+        }
         if (xc.wide) {
             // one pass of 32 threads x K rows per pair (wavefront.cuh), its own profile, list and counters; then the
             // 32-bit recomputation of what it listed, same shape
             const Config c = {32, xc.K, 1, false};
-            cudaError_t e = launch_build_profile(ctx->d_queries.as<int8_t>() + ctx->q_off[q], ctx->q_len[q], ctx->d_submat.as<int8_t>(),
-                                                 32, xc.K, 1, ctx->d_profile_xw.as<uint8_t>(), st);
-            if (e != cudaSuccess) return e;
+            cudaError_t e = cudaSuccess;
             WfParams x = p;
             x.scores = sc;
             x.profile = ctx->d_profile_xw.as<uint8_t>();
@@ -1178,14 +1194,13 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             x.resc_list = ctx->d_xw_list.as<uint32_t>();
             uint64_t tasks = (uint64_t)x.tile_count * kTilePairs;
             if (vt_of[q].second) {
-                // column chunks instead of whole tiles: scores merged with atomicMax, hence zeroed first
+                // column chunks instead of whole tiles (scores merged with atomicMax: zeroed in phase 0)
                 x.vt = ctx->d_vt.as<uint4>() + vt_of[q].first;
                 x.vt_count = (uint32_t)vt_of[q].second;
                 tasks = (uint64_t)x.vt_count * kTilePairs;
-                e = cudaMemsetAsync(sc + (size_t)fl * kTileSeqs, 0, (size_t)(ctx->ntiles - fl) * kTileSeqs * sizeof(int32_t), st);
-                if (e != cudaSuccess) return e;
             }
             xgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)xgrid, (tasks + 15) / 16));
+            long_ctas = xgrid;
             e = launch_wavefront(false, c, xgrid, st, x);
             x.vt = nullptr;
             x.vt_count = 0;
@@ -1199,11 +1214,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             for (uint32_t t = fl; t < ctx->ntiles; ++t) padded += (uint64_t)32 * xc.K * (ctx->h_tile_cols[t] + 31) * kTileSeqs;
             return e;
         }
-        cudaError_t e = launch_build_profile(ctx->d_queries.as<int8_t>() + ctx->q_off[q], ctx->q_len[q], ctx->d_submat.as<int8_t>(),
-                                             32, xc.K, (uint32_t)xc.W, ctx->d_profile_xw.as<uint8_t>(), st);
-        if (e == cudaSuccess)
-            e = cudaMemsetAsync(sc + (size_t)fl * kTileSeqs, 0, (size_t)(ctx->ntiles - fl) * kTileSeqs * sizeof(int32_t), st);
-        if (e != cudaSuccess) return e;
+        cudaError_t e = cudaSuccess;
         WfParams x = p;
         x.scores = sc;
         x.profile = ctx->d_profile_xw.as<uint8_t>();
@@ -1217,6 +1228,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         x.xw_groups = (uint32_t)xc.groups;
         // no more CTAs than there are pairs to keep their groups busy
         xgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)xgrid, ((uint64_t)x.tile_count * kTilePairs + xc.groups - 1) / xc.groups));
+        long_ctas = xgrid;
         e = launch_xw_l16(xc.K, xgrid, st, x);
         mark("long tiles: long-sequence kernel", st);
         x.task_counter = xcnt + 2;
@@ -1267,14 +1279,16 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             cudaStream_t ks = ctx->stream;               // stream of the pair kernel's launches
             bool forked = false;
             if (main_tiles < ctx->ntiles) {
-                if (main_tiles) {
+                e = enqueue_xw(it.members[0], main_tiles, item_long_grid[ii], ctx->stream, 0);
+                if (e == cudaSuccess && main_tiles) {
                     e = cudaEventRecord(ctx->ev_fork, ctx->stream);
                     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
                     forked = e == cudaSuccess;
                     if (forked) ks = ctx->side_stream;
                 }
-                for (size_t k = 0; k < it.members.size() && e == cudaSuccess; ++k)
-                    e = enqueue_xw(it.members[k], main_tiles, item_long_grid[ii], ctx->stream);
+                if (e == cudaSuccess) e = enqueue_xw(it.members[0], main_tiles, item_long_grid[ii], ctx->stream, 1);
+                for (size_t k = 1; k < it.members.size() && e == cudaSuccess; ++k)
+                    e = enqueue_xw(it.members[k], main_tiles, item_long_grid[ii], ctx->stream, 2);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "long-sequence kernel launch");
             }
             auto lane_q = [&](const LaneSlice &sl) { return sl.q >= 0 ? ctx->d_queries.as<int8_t>() + ctx->q_off[sl.q] : nullptr; };
@@ -1375,13 +1389,14 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         if (e == cudaSuccess && first_long < ctx->ntiles) {
             main_tiles = first_long;
             const uint32_t long_tiles = ctx->ntiles - first_long;
-            if (main_tiles) {
+            if (use_xw && e == cudaSuccess) e = enqueue_xw(q, first_long, item_long_grid[ii], ctx->stream, 0);
+            if (main_tiles && e == cudaSuccess) {
                 e = cudaEventRecord(ctx->ev_fork, ctx->stream);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
                 forked = e == cudaSuccess;
             }
             if (use_xw) {
-                if (e == cudaSuccess) e = enqueue_xw(q, first_long, item_long_grid[ii], ctx->stream);
+                if (e == cudaSuccess) e = enqueue_xw(q, first_long, item_long_grid[ii], ctx->stream, 1);
             } else {
                 const uint64_t long_warps = (uint64_t)long_tiles * kTilePairs;          // one pair per warp at G = 32
                 const int long_grid = long_grid_for(first_long, (long_warps + warps_per_block - 1) / warps_per_block, main_tiles > 0);
@@ -1405,10 +1420,21 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             p.tile_count = main_tiles;
             p.task_counter = cnt + 1;
             mark("before the sequence-pair kernel", forked ? ctx->side_stream : ctx->stream);
-            e = launch_wavefront(false, main_cfg, grid, forked ? ctx->side_stream : ctx->stream, p);
+            // With long tiles running beside it the main kernel leaves them their SMs (its CTAs are persistent: had it
+            // taken every SM first, the long tiles would wait for all of it), and a second wave of the same kernel --
+            // same task counter -- follows the long tiles on their stream and takes over their SMs when they are done.
+            const int wave2 = (forked && use_xw && long_ctas > 0 && long_ctas < grid) ? long_ctas : 0;
+            e = launch_wavefront(false, main_cfg, grid - wave2, forked ? ctx->side_stream : ctx->stream, p);
             mark("sequence-pair kernel", forked ? ctx->side_stream : ctx->stream);
             if (e == cudaSuccess && forked) e = cudaEventRecord(ctx->ev_join, ctx->side_stream);
             ctx->stats.launches += 1;
+            if (e == cudaSuccess && wave2) {
+                WfParams p2 = p;
+                p2.boundary = p.boundary + (size_t)(grid - wave2) * warps_per_block * (size_t)p.maxcols;     // its own scratch lines
+                e = launch_wavefront(false, main_cfg, wave2, ctx->stream, p2);
+                mark("sequence-pair kernel, second wave", ctx->stream);
+                ctx->stats.launches += 1;
+            }
         }
         if (e == cudaSuccess && forked) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
         mark("joined", ctx->stream);

@@ -4,7 +4,30 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace swg {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize of a kernel, set once per (device, kernel) and raised when a launch needs
+// more: the driver call is too slow to repeat on every launch (it can block for a millisecond, which a 1 ms search
+// shows as GPU idle time), and the bookkeeping must be safe with one host thread per GPU.
+inline cudaError_t ensure_dynamic_smem(const void *kernel, size_t bytes)
+{
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &have = done[std::make_pair(dev, kernel)];
+    if (bytes <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
 
 // ---- device database layout --------------------------------------------------------------------
 // Sorted sequences are grouped 16 to a TILE (8 PAIRS).  All 16 are padded to the tile's column

@@ -352,13 +352,8 @@ cudaError_t launch_wf_l32_gp(int grid, cudaStream_t stream, const WfParams &p);
 template <class L, int G, int K, bool MP, bool GP, int GOE = 0, int GE = 0>
 cudaError_t launch_one(int grid, size_t smem, cudaStream_t stream, const WfParams &p)
 {
-    // the attribute lives in the device's context; setting it on every launch is a cheap driver call and keeps the
-    // launcher free of shared state (one context per host thread is allowed)
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(wavefront_kernel<L, G, K, MP, GP, GOE, GE>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(&wavefront_kernel<L, G, K, MP, GP, GOE, GE>), smem);
+    if (e != cudaSuccess) return e;
     wavefront_kernel<L, G, K, MP, GP, GOE, GE><<<grid, kBlockThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }

@@ -267,9 +267,7 @@ cudaError_t launch_q2_g32_last(int K, int grid, cudaStream_t stream, const WfPar
 template <int G, int K, bool CIN, bool COUT, int GOE = 0, int GE = 0>
 cudaError_t launch_q2_one(int grid, cudaStream_t stream, const WfParams &p)
 {
-    // set on every launch (cheap, and no state shared between host threads driving different GPUs)
-    cudaError_t e = cudaFuncSetAttribute(wavefront_q2_kernel<G, K, CIN, COUT, GOE, GE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kQ2ProfileBytes);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(&wavefront_q2_kernel<G, K, CIN, COUT, GOE, GE>), kQ2ProfileBytes);
     if (e != cudaSuccess) return e;
     wavefront_q2_kernel<G, K, CIN, COUT, GOE, GE><<<grid, kBlockThreads, kQ2ProfileBytes, stream>>>(p);
     return cudaGetLastError();

@@ -354,10 +354,8 @@ inline size_t xw_smem_bytes(int K, int W)
 template <class L, int K, int GOE = 0, int GE = 0>
 cudaError_t launch_xw_one(int grid, cudaStream_t stream, const WfParams &p)
 {
-    // the attribute is set on every launch: it is a cheap driver call, and it keeps the launcher free of per-device state
     const size_t smem = xw_smem_bytes(K, (int)p.xw_warps);
-    cudaError_t e = cudaFuncSetAttribute(wavefront_xw_kernel<L, K, GOE, GE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(&wavefront_xw_kernel<L, K, GOE, GE>), smem);
     if (e != cudaSuccess) return e;
     wavefront_xw_kernel<L, K, GOE, GE><<<grid, kBlockThreads, smem, stream>>>(p);
     return cudaGetLastError();
