@@ -579,16 +579,19 @@ def other_configs(s, gpu, peaks):
             s.run(TOP)
             s.sync()
         timed_steps(s, one, 0, warm)
-        dev, qs = 0.0, np.zeros(w.q.n)
+        dev, srch, qs = 0.0, 0.0, np.zeros(w.q.n)
         for _ in range(steps):
             one()
             dev += s.stats()["device_seconds"]
+            srch += s.stats()["search_seconds"]
             qs += s.query_seconds()
         kinds = s.query_kernels()
         share1 = float(qs[kinds == 1].sum()) / max(float(qs.sum()), 1e-12)
         kind = 1 if share1 >= 0.5 else 0
-        gc = w.cells * steps / dev / 1e9
+        gc = w.cells * steps / dev / 1e9           # the whole step: search kernels + top-r
+        kgc = w.cells * steps / srch / 1e9        # the search kernels alone (what the roofline fraction is about)
         rec = {"workload": w.describe() + ", %s, gap %d/%d" % (matrix, go, ge), "gcups": gc, "ms_per_step": dev / steps * 1e3,
+               "search_kernels_gcups": kgc, "search_ms_per_step": srch / steps * 1e3,
                "sm_mhz_after": sm_clock_mhz(0),
                "dominant_kernel": KERNELS[kind][1], "share_of_search_time": share1 if kind else 1.0 - share1}
         if peaks:
@@ -596,7 +599,8 @@ def other_configs(s, gpu, peaks):
             if not fast and generic_peaks is None:
                 generic_peaks = kernel_peaks(s.pipebench(), False)
             pk = peaks[kind] if fast else generic_peaks[kind]
-            rec.update({"peak": pk["peak"], "frac": gc / pk["peak"], "frac_strict_alu_pipe": gc / pk["peak_strict"]})
+            rec.update({"peak": pk["peak"], "frac": kgc / pk["peak"], "frac_strict_alu_pipe": kgc / pk["peak_strict"],
+                        "frac_whole_step": gc / pk["peak"]})
         out["%s %s %d/%d" % (name, matrix, go, ge)] = rec
         log("[config] %s %s %d/%d: %.0f GCUPS" % (name, matrix, go, ge, gc))
     return out

@@ -249,8 +249,11 @@ TopkPlan topk_plan(uint64_t n_pad, uint64_t top, uint64_t q_count)
         pl.nslices = 0;
         pl.scratch_keys = pow2_at_least(n_pad < 2048 ? 2048 : n_pad);
     } else {
-        uint64_t slice = 16 * top;
-        if (slice < 8192) slice = 8192;
+        // slices of 8192 scores; smaller ones (down to 1024) when the batch would otherwise not fill the GPU with blocks
+        // (a single short search: the selection is latency-bound, more blocks in parallel shorten it)
+        uint64_t slice = 8192;
+        while (slice > 1024 && (n_pad + slice - 1) / slice * q_count < 296) slice /= 2;
+        if (slice < 16 * top) slice = 16 * top;
         pl.slice = (uint32_t)slice;
         pl.nslices = (uint32_t)((n_pad + slice - 1) / slice);
         if (pl.nslices == 0) pl.nslices = 1;
