@@ -148,7 +148,7 @@ int swg_plan_describe(const uint16_t *q_lengths, uint64_t q_count, uint64_t n_se
 
 /* Measured issue rates of the search kernel's instruction mix (the integer roofline the search is
  * reported against).  ginstr_per_s[p] = 1e9 thread-instructions per second on the whole GPU for probe p,
- * sm_mhz[p] = the SM clock during it, names[p] = static strings.  max_probes >= 32 is enough. */
+ * sm_mhz[p] = the SM clock during it, names[p] = static strings.  max_probes >= 64 is enough. */
 int swg_gpu_pipebench(swg_ctx *ctx, int max_probes, double *ginstr_per_s, double *sm_mhz, const char **names,
                       int *n_probes, int *sm_count);
 

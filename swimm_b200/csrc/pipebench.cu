@@ -30,7 +30,7 @@ enum Probe {
     P_HFMA2, P_HMNMX2, P_IDP4A, P_MIX65, P_MIX55_IMAD, P_PAIR_DPX_IMAD, P_PAIR_DPX_HFMA2, P_PAIR_DPX_PRMT,
     P_PAIR_DPX_IDP, P_SHFL, P_LDS128, P_PAIR_DPX_SHFL, P_PAIR_DPX_LDS, P_MIX_V2, P_PAIR_DPX_VIADD, P_PAIR_DPX_HMNMX2,
     P_PAIR_DPX_FFMA, P_PAIR_VIADD_IMAD, P_MIX_A, P_MIX_B, P_MIX_C, P_PAIR_MAX3_VIADD, P_PAIR_PRMT_VIADD,
-    P_MIX_V2_IMM, P_MIX_Q2_IMM, P_COUNT
+    P_MIX_V2_IMM, P_MIX_Q2_IMM, P_MIX_V2_GE_IMM, P_MIX_Q2_GE_IMM, P_COUNT
 };
 
 const char *const kProbeName[P_COUNT] = {
@@ -40,12 +40,13 @@ const char *const kProbeName[P_COUNT] = {
     "pair_viaddmnmx_shfl", "pair_viaddmnmx_lds128", "mix_v2_4p5_alu_2_viadd", "pair_viaddmnmx_viadd16x2",
     "pair_viaddmnmx_hmnmx2", "pair_viaddmnmx_ffma", "pair_viadd16x2_imad", "mix_a_hef_3alu_2viadd",
     "mix_b_hef_prmt_4alu_2viadd", "mix_c_hef_best_3p5alu_2viadd", "pair_vimnmx3_viadd16x2", "pair_prmt_viadd16x2",
-    "mix_v2_immediate_penalties", "mix_q2_3p5alu_2viadd_immediate"};
+    "mix_v2_immediate_penalties", "mix_q2_3p5alu_2viadd_immediate", "mix_v2_extend_immediate_open_register",
+    "mix_q2_extend_immediate_open_register"};
 
 // thread-instructions counted per inner step of one chain
 __host__ __device__ constexpr double probe_instr(int p)
 {
-    return p == P_MIX65 ? 6.5 : p == P_MIX_V2 ? 6.5 : p == P_MIX_V2_IMM ? 6.5 : p == P_MIX_A ? 5.0 : p == P_MIX_B ? 6.0 : p == P_MIX_C ? 5.5 : p == P_MIX_Q2_IMM ? 5.5 :
+    return p == P_MIX65 ? 6.5 : p == P_MIX_V2 ? 6.5 : p == P_MIX_V2_IMM ? 6.5 : p == P_MIX_V2_GE_IMM ? 6.5 : p == P_MIX_Q2_GE_IMM ? 5.5 : p == P_MIX_A ? 5.0 : p == P_MIX_B ? 6.0 : p == P_MIX_C ? 5.5 : p == P_MIX_Q2_IMM ? 5.5 :
            (p == P_PAIR_MAX3_VIADD || p == P_PAIR_PRMT_VIADD) ? 2.0 : (p >= P_PAIR_DPX_VIADD && p <= P_PAIR_VIADD_IMAD) ? 2.0 : p == P_MIX55_IMAD ? 6.5 : p == P_IADD3 ? 0.5 : (p >= P_PAIR_DPX_IMAD && p <= P_PAIR_DPX_IDP) ? 2.0
          : (p == P_PAIR_DPX_SHFL || p == P_PAIR_DPX_LDS) ? 2.0 : 1.0;
 }
@@ -156,17 +157,21 @@ probe_kernel(uint32_t *out, uint32_t iters, const uint32_t *consts, long long *c
                     g[c] = ds;
                     d[c] = v[c];
                     v[c] = h;
-                } else if (P == P_MIX_A || P == P_MIX_B || P == P_MIX_C || P == P_MIX_V2_IMM || P == P_MIX_Q2_IMM) {
+                } else if (P == P_MIX_A || P == P_MIX_B || P == P_MIX_C || P == P_MIX_V2_IMM || P == P_MIX_Q2_IMM || P == P_MIX_V2_GE_IMM ||
+                           P == P_MIX_Q2_GE_IMM) {
                     uint32_t s = e[c] ^ 0u;
-                    if (P == P_MIX_B || P == P_MIX_V2_IMM) s = prmt(e[c], f[c], 0xc480 + (u & 3) * 0x1111);
+                    if (P == P_MIX_B || P == P_MIX_V2_IMM || P == P_MIX_V2_GE_IMM) s = prmt(e[c], f[c], 0xc480 + (u & 3) * 0x1111);
                     else s = g[c];
                     const uint32_t ds = __vadd2(d[c], s);
                     const uint32_t h = __vimax3_s16x2_relu(ds, e[c], f[c]);
                     constexpr bool IMM = (P == P_MIX_V2_IMM || P == P_MIX_Q2_IMM);
+                    // only the gap-EXTEND penalty as an immediate (it is the third operand of the two VIADDMNMX), the
+                    // gap-open term from a register (second operand of a VIADD.16x2)
+                    constexpr bool GE_IMM = (P == P_MIX_V2_GE_IMM || P == P_MIX_Q2_GE_IMM);
                     const uint32_t open = IMM ? __vadd2(h, 0xfff4fff4u) : __vadd2(h, k1);
-                    e[c] = IMM ? __viaddmax_s16x2(e[c], 0xfffefffeu, open) : __viaddmax_s16x2(e[c], k2, open);
-                    f[c] = IMM ? __viaddmax_s16x2(f[c], 0xfffefffeu, open) : __viaddmax_s16x2(f[c], k2, open);
-                    if ((P == P_MIX_C || IMM) && (u & 1)) b[c] = __vimax3_s16x2(b[c], g[c], ds);
+                    e[c] = (IMM || GE_IMM) ? __viaddmax_s16x2(e[c], 0xfffefffeu, open) : __viaddmax_s16x2(e[c], k2, open);
+                    f[c] = (IMM || GE_IMM) ? __viaddmax_s16x2(f[c], 0xfffefffeu, open) : __viaddmax_s16x2(f[c], k2, open);
+                    if ((P == P_MIX_C || IMM || GE_IMM) && (u & 1)) b[c] = __vimax3_s16x2(b[c], g[c], ds);
                     if (P != P_MIX_A && P != P_MIX_B) g[c] = ds;
                     d[c] = v[c];
                     v[c] = h;

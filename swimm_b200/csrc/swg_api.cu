@@ -878,9 +878,14 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 fl = (uint32_t)(std::upper_bound(ctx->h_tile_cols_mono.begin(), ctx->h_tile_cols_mono.end(),
                                                  (uint32_t)std::min(limit, 4.0e9)) - ctx->h_tile_cols_mono.begin());
             if (fl >= ctx->ntiles) continue;
+            // outliers only: at most the longest 30 % of the shard's columns leave the main launches (a small shard is
+            // "long" as a whole by the column limit; its bulk still belongs on the main kernels)
+            if (!forced && total_cols - (double)ctx->h_cols_prefix[fl] > 0.3 * total_cols) {
+                const uint64_t keep = (uint64_t)(0.7 * total_cols);
+                fl = (uint32_t)(std::lower_bound(ctx->h_cols_prefix.begin(), ctx->h_cols_prefix.end(), keep) - ctx->h_cols_prefix.begin());
+                fl = std::min(fl, ctx->ntiles - 1);
+            }
             const double long_cols = total_cols - (double)ctx->h_cols_prefix[fl];
-            // outliers only: a shard that is "long" as a whole stays on the main kernels
-            if (!forced && long_cols > 0.3 * total_cols) continue;
             if (!xw_ok) {
                 // queries the long-sequence kernel does not cover (or long_kernel = 0): a single query falls back to the
                 // 32-thread shape of its own kernel, a query group keeps every tile
@@ -1034,9 +1039,11 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         w.resc_count2 = ctx->d_counters.as<uint32_t>() + 1;
         w.passes = 1;
         cudaError_t we = cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(uint32_t), ctx->stream);
-        const uint32_t fast = (w.gap_open_extend == kFastGapOpenExtend && w.gap_extend == kFastGapExtend) ? 1u : 0u;
+        // which instantiation family the penalties select: defaults as immediates, gap-extend 1 or 2 as an immediate, generic
+        const uint32_t fast = (w.gap_open_extend == kFastGapOpenExtend && w.gap_extend == kFastGapExtend) ? 1u
+                              : w.gap_extend == 1 ? 2u : w.gap_extend == 2 ? 3u : 0u;
         auto fresh = [&](uint32_t key) {
-            key = key * 2 + fast;
+            key = key * 4 + fast;
             if (std::find(ctx->warmed.begin(), ctx->warmed.end(), key) != ctx->warmed.end()) return false;
             ctx->warmed.push_back(key);
             return true;

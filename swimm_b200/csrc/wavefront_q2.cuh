@@ -67,7 +67,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
     const int t = lane % G;
     const int g = lane / G;
     const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const reg nge = GOE > 0 ? L::splat(-GE) : L::splat(-p.gap_extend);
+    // GE > 0: the gap-extend penalty is an immediate (it is the third operand of the two VIADDMNMX per cell: with it in
+    // a register they read three registers and take two register-bank cycles); GOE > 0: go + ge as an immediate too
+    // (second operand of a VIADD.16x2: no difference in rate, kept for SWIMM's defaults)
+    const reg nge = GE > 0 ? L::splat(-GE) : L::splat(-p.gap_extend);
     const reg ngoe = GOE > 0 ? L::splat(-GOE) : L::splat(-p.gap_open_extend);
     const uint32_t pad_pk = 0x00006000u;
     const uint32_t ntasks = p.tile_count * TPT;
@@ -280,6 +283,25 @@ cudaError_t launch_q2_family(int K, int grid, cudaStream_t stream, const WfParam
     if (p.gap_open_extend == FO && p.gap_extend == FE) {
         switch (K) {
 #define SWG_CASE(k) case k: return launch_q2_one<G, k, CIN, COUT, FO, FE>(grid, stream, p);
+            SWG_CASE(8) SWG_CASE(10) SWG_CASE(12) SWG_CASE(14) SWG_CASE(16) SWG_CASE(18) SWG_CASE(20)
+            SWG_CASE(22) SWG_CASE(24) SWG_CASE(26) SWG_CASE(28) SWG_CASE(30) SWG_CASE(32)
+#undef SWG_CASE
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    // gap-extend penalties 1 and 2 (with any gap-open penalty) cover BLAST's, SSEARCH's and SWIMM's usual settings
+    if (p.gap_extend == 1) {
+        switch (K) {
+#define SWG_CASE(k) case k: return launch_q2_one<G, k, CIN, COUT, 0, 1>(grid, stream, p);
+            SWG_CASE(8) SWG_CASE(10) SWG_CASE(12) SWG_CASE(14) SWG_CASE(16) SWG_CASE(18) SWG_CASE(20)
+            SWG_CASE(22) SWG_CASE(24) SWG_CASE(26) SWG_CASE(28) SWG_CASE(30) SWG_CASE(32)
+#undef SWG_CASE
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    if (p.gap_extend == 2) {
+        switch (K) {
+#define SWG_CASE(k) case k: return launch_q2_one<G, k, CIN, COUT, 0, 2>(grid, stream, p);
             SWG_CASE(8) SWG_CASE(10) SWG_CASE(12) SWG_CASE(14) SWG_CASE(16) SWG_CASE(18) SWG_CASE(20)
             SWG_CASE(22) SWG_CASE(24) SWG_CASE(26) SWG_CASE(28) SWG_CASE(30) SWG_CASE(32)
 #undef SWG_CASE
