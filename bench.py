@@ -419,7 +419,7 @@ def main():
     roof, peaks = None, None
     if rank == 0 and not args.no_pipebench:
         roof = roofline(s, gpu, q_secs, ql, len(dc), args.steps, st, search_s, cells_local, dev_s)
-        peaks = roof.pop("_peaks")
+        peaks = (roof.pop("_peaks"), roof.pop("_pb"))
 
     # ---- strong scaling + the other BASELINE configurations, measured in the same run ----
     strong, configs = None, None
@@ -492,31 +492,35 @@ def main():
 
 
 KERNELS = [
-    # kind, name, pipebench probe (default penalties as immediates / generic), instr per 2 cells, ALU-pipe instr per 2 cells
+    # kind, name, pipebench probes (default penalties as immediates / gap-extend as an immediate / generic), instr per
+    # 2 cells, ALU-pipe instr per 2 cells
     (0, "wavefront_kernel<Lane16,G,K> (one query x two database sequences per register)",
-     ("mix_v2_immediate_penalties", "mix_v2_4p5_alu_2_viadd"), 6.5, 4.5,
+     ("mix_v2_immediate_penalties", None, "mix_v2_4p5_alu_2_viadd"), 6.5, 4.5,
      "6.5 integer instr per 2 cells: 4.5 on the ALU pipe (PRMT, VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + 2 VIADD.16x2"),
     (1, "wavefront_q2_kernel<G,K> (two queries x one database sequence per register)",
-     ("mix_q2_3p5alu_2viadd_immediate", "mix_c_hef_best_3p5alu_2viadd"), 5.5, 3.5,
+     ("mix_q2_3p5alu_2viadd_immediate", "mix_q2_extend_immediate_open_register", "mix_c_hef_best_3p5alu_2viadd"), 5.5, 3.5,
      "5.5 integer instr per 2 cells: 3.5 on the ALU pipe (VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + 2 VIADD.16x2"),
 ]
 
 
-def kernel_peaks(pb, fast):
-    """Per kernel: peak GCUPS of its own measured dependency-free mix, and the strict ALU-pipe bound (64 lanes/clk/SM)."""
+def kernel_peaks(pb, go, ge):
+    """Per kernel: peak GCUPS of its own measured dependency-free mix -- the instantiation family the penalties select:
+    SWIMM's defaults (10/2) as immediates, gap-extend 1 or 2 as an immediate (query-pair kernel), or penalties in
+    registers -- and the strict ALU-pipe bound (64 lanes/clk/SM)."""
     out = {}
     for kind, name, probes, ipc2, alu2, mix_text in KERNELS:
-        mix = pb["probes"][probes[0] if fast else probes[1]]
+        probe = probes[0] if (go + ge, ge) == (12, 2) else probes[1] if (ge in (1, 2) and probes[1]) else probes[2]
+        mix = pb["probes"][probe]
         strict = pb["sms"] * mix["sm_mhz"] * 1e6 * 64.0 * 2.0 / alu2 / 1e9
         out[kind] = {"name": name, "peak": mix["ginstr_per_s"] * 2.0 / ipc2, "peak_strict": strict,
-                     "mix": mix_text + "; measured %.1f thread-instr/clk/SM at %.0f MHz"
-                            % (mix["thread_instr_per_clk_per_sm"], mix["sm_mhz"])}
+                     "mix": mix_text + "; probe %s: measured %.1f thread-instr/clk/SM at %.0f MHz"
+                            % (probe, mix["thread_instr_per_clk_per_sm"], mix["sm_mhz"])}
     return out
 
 
 def roofline(s, gpu, q_secs, ql, residues, steps, st, search_s, cells_local, dev_s):
     pb = s.pipebench()
-    peaks = kernel_peaks(pb, (GO + GE, GE) == (12, 2))
+    peaks = kernel_peaks(pb, GO, GE)
     kinds = s.query_kernels()
     kernels = {}
     for kind, pk in peaks.items():
@@ -557,14 +561,13 @@ def roofline(s, gpu, q_secs, ql, residues, steps, st, search_s, cells_local, dev
             "hbm": {"bound": "hbm", "achieved": algo_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": algo_gbs / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if have_peaks else "fallback"},
             "pipebench": {k: round(v["thread_instr_per_clk_per_sm"], 2) for k, v in pb["probes"].items()},
-            "_peaks": peaks}
+            "_peaks": peaks, "_pb": pb}
 
 
 def other_configs(s, gpu, peaks):
     """BASELINE.json configs[0], [3], [4] on this GPU, after the headline: GCUPS of the whole batch, which kernel took most
     of the time and the fraction of that kernel's roofline."""
     out = {}
-    generic_peaks = None
     runs = [("cfg1", "blosum62", 10, 2, 20, 5), ("cfg4", "blosum62", 10, 2, 3, 2),
             ("cfg5", "blosum45", 8, 2, 10, 3), ("cfg5", "pam250", 12, 1, 10, 3)]
     loaded = None
@@ -595,12 +598,9 @@ def other_configs(s, gpu, peaks):
                "sm_mhz_after": sm_clock_mhz(0),
                "dominant_kernel": KERNELS[kind][1], "share_of_search_time": share1 if kind else 1.0 - share1}
         if peaks:
-            fast = (go + ge, ge) == (12, 2)
-            if not fast and generic_peaks is None:
-                generic_peaks = kernel_peaks(s.pipebench(), False)
-            pk = peaks[kind] if fast else generic_peaks[kind]
+            pk = kernel_peaks(peaks[1], go, ge)[kind]
             rec.update({"peak": pk["peak"], "frac": kgc / pk["peak"], "frac_strict_alu_pipe": kgc / pk["peak_strict"],
-                        "frac_whole_step": gc / pk["peak"]})
+                        "frac_whole_step": gc / pk["peak"], "mix": pk["mix"]})
         out["%s %s %d/%d" % (name, matrix, go, ge)] = rec
         log("[config] %s %s %d/%d: %.0f GCUPS" % (name, matrix, go, ge, gc))
     return out

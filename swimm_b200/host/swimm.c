@@ -75,6 +75,23 @@ static void batch_free(batch *b)
     memset(b, 0, sizeof(*b));
 }
 
+typedef struct {
+    batch *b;
+    swg_ctx *ctx;
+    const swg_options *opt;
+    unsigned long top;
+    int *ticket;
+    int st;
+} submit_job;
+
+static void *submit_thread(void *arg)
+{
+    submit_job *j = (submit_job *)arg;
+    j->st = swg_gpu_submit(j->ctx, j->b->q.codes, j->b->q.lengths, j->b->q_disp, j->b->q.count, swg_submat_table(j->opt->submat),
+                           j->opt->open_gap, j->opt->extend_gap, j->top, j->ticket);
+    return NULL;
+}
+
 /* parse a query file and queue it on every GPU; returns 0, or the reference's exit code */
 static int batch_submit(batch *b, const char *qfile, swg_ctx **ctx, int ngpu, const swg_options *opt, unsigned long top)
 {
@@ -117,13 +134,29 @@ static int batch_submit(batch *b, const char *qfile, swg_ctx **ctx, int ngpu, co
         }
         return 0;
     }
-    /* every GPU gets all queries and searches its shard of the database */
+    /* every GPU gets all queries and searches its shard of the database; one host thread per GPU queues the batch
+     * (planning, the first call's one-off loading of the kernels' code) so that no device waits for another's host work */
+    submit_job *jobs = (submit_job *)calloc((size_t)ngpu, sizeof(submit_job));
+    pthread_t *threads = (pthread_t *)calloc((size_t)ngpu, sizeof(pthread_t));
     for (int g = 0; g < ngpu; g++) {
-        int st = swg_gpu_submit(ctx[g], b->q.codes, b->q.lengths, b->q_disp, b->q.count, swg_submat_table(opt->submat),
-                                opt->open_gap, opt->extend_gap, top, &b->tickets[g]);
-        if (st != SWG_OK)
-            die_gpu("search", ctx[g], st);
+        jobs[g].b = b;
+        jobs[g].ctx = ctx[g];
+        jobs[g].opt = opt;
+        jobs[g].top = top;
+        jobs[g].ticket = &b->tickets[g];
+        if (ngpu == 1 || pthread_create(&threads[g], NULL, submit_thread, &jobs[g]) != 0) {
+            submit_thread(&jobs[g]);
+            threads[g] = 0;
+        }
     }
+    for (int g = 0; g < ngpu; g++) {
+        if (threads[g])
+            pthread_join(threads[g], NULL);
+        if (jobs[g].st != SWG_OK)
+            die_gpu("search", ctx[g], jobs[g].st);
+    }
+    free(jobs);
+    free(threads);
     return 0;
 }
 

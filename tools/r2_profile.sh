@@ -12,10 +12,10 @@ CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-pipebench --no-
 $CMD > $O/prof3_plain.json 2> $O/prof3_plain.err || exit 1
 i=0
 for pat in "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.0, .bool.1" "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.1, .bool.1" "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.1, .bool.0" "wavefront_kernel<swg::Lane16, .int.8, "; do
-  i=$((i+1))
+  i=$((i+1)); SKIP=10; if [ $i = 4 ]; then SKIP=3; fi
   if [ -n "$ONLY" ] && [ "$ONLY" != "$i" ]; then continue; fi
   # the first launches of every instantiation are the empty warm-up launches of the first run: skip past them
-  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"$pat" -s 10 -c 1 -f -o $O/prof3_$i $CMD > $O/ncu3_$i.log 2>&1
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"$pat" -s $SKIP -c 1 -f -o $O/prof3_$i $CMD > $O/ncu3_$i.log 2>&1
   echo "capture $i exit $?"
 done
 CMD="python tools/xw_profile_target.py"
