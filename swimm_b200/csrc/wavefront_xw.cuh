@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_xw_kernel(const Wf
 {
     typedef typename L::reg reg;
     static_assert(K >= 1 && K <= kMaxRowsPerThread, "rows per thread");
-    static_assert(kBlockThreads == 512, "16 warps per CTA");
+    static_assert(kBlockThreads % 32 == 0, "whole warps");      // (the planner assumes 16 warps per CTA: experimental CTA sizes do not run this kernel)
     constexpr int G = 32;
     constexpr int TPT = kTilePairs;                   // Lane16: one pair per group and task
     constexpr int KCH = (K + 15) / 16;                // 16-row profile chunks per thread

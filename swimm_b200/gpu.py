@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswimm_cuda.so")
+# (SWIMM_B200_LIB: an experimental build of the same library, e.g. another CTA size: tools only)
+LIB_PATH = os.environ.get("SWIMM_B200_LIB") or os.path.join(_HERE, "libswimm_cuda.so")
 
 # every symbol include/swimm_gpu.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [

@@ -221,9 +221,10 @@ static void batch_report(batch *b, swg_ctx **ctx, int ngpu, const swg_seqset *db
         }
     }
     free(show);
-    /* Search time: CUDA-event time of the whole batch on the slowest GPU -- wait for the query upload, profile builds,
-     * all search kernels, top-r selection and the hit-list download; the host-side merge of N x top keys is not in it
-     * (the reference's workTime covers its kernel call only, its sort is outside too: swimm.c:151-160) */
+    /* Search time: CUDA-event time of the whole batch on the slowest GPU -- profile builds, all search kernels, top-r
+     * selection and the hit-list download; the one-off loading of kernel code by a process's first batch and the
+     * host-side merge of N x top keys are not in it (the reference's workTime covers its kernel call only, its sort
+     * is outside too: swimm.c:151-160) */
     printf("\nSearch date:\t\t\t%s", ctime(&b->when));
     printf("Search time:\t\t\t%lf seconds\n", work);
     printf("Search speed:\t\t\t%.2lf GCUPS\n", ((double)Q * (double)db->residues) / (work * 1000000000.0));

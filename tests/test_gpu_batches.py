@@ -173,3 +173,43 @@ def test_alignment_coordinates_of_the_hits(gpu, oracle):
                 assert 0 <= c[0] <= c[1] < ql[qi] and 0 <= c[2] <= c[3] < dl[ki[h]]
                 checked += 1
         assert checked >= 30
+
+
+def test_256_queries_one_million_sequences_under_a_score_budget(gpu, oracle):
+    """256 queries x 1 000 000 sequences would keep 1 GB of score rows; under a 256 MB budget the batch is searched in
+    four chunks of 64 queries.  Size-independent checks: the hit lists equal those of the one-piece run (4 GB budget),
+    and -- for a few queries -- the oracle's on a sample of the database that contains all their hits."""
+    from swimm_b200.gpu import split_key
+    rng = np.random.default_rng(77)
+    q = synth.make_queries(rng, list(rng.integers(25, 90, 256)))
+    dl, dc = synth.sorted_db(78, 1_000_000, mu=3.6, sigma=0.4, lo=8, hi=400, queries=q, plant_fraction=0.002)
+    _, ql, qc = synth.length_sorted(q)
+    qo = np.zeros(q.n + 1, np.uint32)
+    np.cumsum(ql.astype(np.uint32), out=qo[1:])
+    b62 = host.submat("blosum62")
+    gpu.load_db(dl, dc)
+    try:
+        gpu.set_option("score_budget_mb", 256)
+        _, chunked = gpu.search(qc, ql, qo[:-1], b62, 10, 2, 10)
+        launches_chunked = gpu.stats()["launches"]
+        gpu.set_option("score_budget_mb", 4096)
+        _, whole = gpu.search(qc, ql, qo[:-1], b62, 10, 2, 10)
+        assert gpu.stats()["launches"] != launches_chunked
+    finally:
+        gpu.set_option("score_budget_mb", 4096)
+    assert np.array_equal(chunked, whole)
+    # oracle on a sample: the hit sequences of five queries + every 500th sequence
+    off = np.zeros(len(dl) + 1, np.int64)
+    np.cumsum(dl.astype(np.int64), out=off[1:])
+    for qi in (0, 63, 64, 200, 255):
+        ks, ki = split_key(chunked[qi])
+        sub = np.unique(np.concatenate([ki, np.arange(0, len(dl), 500)]))
+        sl = dl[sub]
+        so = np.zeros(len(sub) + 1, np.uint64)
+        np.cumsum(sl.astype(np.uint64), out=so[1:])
+        idx = np.repeat(off[sub] - so[:-1].astype(np.int64), sl.astype(np.int64)) + np.arange(int(so[-1]))
+        want = oracle.search(qc[qo[qi]:qo[qi + 1]], np.array([0, ql[qi]], np.uint32), dc[idx], so, b62, 10, 2)[0]
+        pos = {int(g): i for i, g in enumerate(sub)}
+        assert np.array_equal(want[[pos[int(g)] for g in ki]], ks)
+        keys_sub = (want.astype(np.uint64) << np.uint64(32)) | sub.astype(np.uint64)
+        assert np.isin(sub[keys_sub > np.uint64(chunked[qi, -1])], ki).all()
