@@ -495,7 +495,7 @@ KERNELS = [
     # kind, name, pipebench probes (default penalties as immediates / gap-extend as an immediate / generic), instr per
     # 2 cells, ALU-pipe instr per 2 cells
     (0, "wavefront_kernel<Lane16,G,K> (one query x two database sequences per register)",
-     ("mix_v2_immediate_penalties", None, "mix_v2_4p5_alu_2_viadd"), 6.5, 4.5,
+     ("mix_v2_immediate_penalties", "mix_v2_extend_immediate_open_register", "mix_v2_4p5_alu_2_viadd"), 6.5, 4.5,
      "6.5 integer instr per 2 cells: 4.5 on the ALU pipe (PRMT, VIMNMX3.RELU, VIADDMNMX x2, VIMNMX3/2) + 2 VIADD.16x2"),
     (1, "wavefront_q2_kernel<G,K> (two queries x one database sequence per register)",
      ("mix_q2_3p5alu_2viadd_immediate", "mix_q2_extend_immediate_open_register", "mix_c_hef_best_3p5alu_2viadd"), 5.5, 3.5,

@@ -41,7 +41,8 @@ constexpr uint32_t kMarkTask = 2u;      // ... and it is the first pass of a new
 constexpr uint32_t kMarkCarry = 4u;     // the segment is not the task's last pass: the last row goes to the scratch line
 
 // GOE/GE > 0: the gap penalties are compile-time constants and become immediate operands (fewer register-file
-// reads per cell: pipebench mix_v2_immediate_penalties vs mix_v2); 0: taken from the parameter block.
+// reads per cell: pipebench mix_v2_immediate_penalties vs mix_v2); 0: taken from the parameter block.  Instantiated:
+// (12, 2) = SWIMM's defaults, (0, 1) and (0, 2) = gap-extend 1 or 2 with any gap-open, (0, 0) = generic.
 template <class L, int G, int K, bool MP, bool GP, int GOE, int GE>
 __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfParams p)
 {
@@ -76,7 +77,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_kernel(const WfPar
     const int g = lane / G;
     const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     uint2 *bnd = p.boundary + (size_t)warp_global * p.maxcols;
-    const reg nge = GOE > 0 ? L::splat(-GE) : L::splat(-p.gap_extend);
+    // GE > 0: the gap-extend penalty as an immediate -- it is the third operand of the two VIADDMNMX per cell, which
+    // with it in a register read three registers (two register-bank cycles); GOE > 0: go + ge as an immediate too
+    const reg nge = GE > 0 ? L::splat(-GE) : L::splat(-p.gap_extend);
     const reg ngoe = GOE > 0 ? L::splat(-GOE) : L::splat(-p.gap_open_extend);
     const uint32_t npass = MP ? p.passes : 1u;
     const uint32_t pad_pk = (L::kSeqs == 2) ? 0x60006000u : 0x00006000u;

@@ -17,6 +17,22 @@ cudaError_t launch_wf_l16_g32_mp(int K, int grid, size_t smem, cudaStream_t stre
             default: return cudaErrorInvalidValue;
         }
     }
+    if (p.gap_extend == 1) {            // gap-extend penalty as an immediate, any gap-open penalty (see wavefront.cuh)
+        switch (K) {
+#define SWG_CASE(k) case k: return launch_one<Lane16, 32, k, true, false, 0, 1>(grid, smem, stream, p);
+            SWG_CASE(1) SWG_CASE(2) SWG_CASE(3) SWG_CASE(4) SWG_CASE(5) SWG_CASE(6) SWG_CASE(7) SWG_CASE(8) SWG_CASE(9) SWG_CASE(10) SWG_CASE(11) SWG_CASE(12) SWG_CASE(13) SWG_CASE(14) SWG_CASE(15) SWG_CASE(16) SWG_CASE(17) SWG_CASE(18) SWG_CASE(19) SWG_CASE(20) SWG_CASE(21) SWG_CASE(22) SWG_CASE(23) SWG_CASE(24) SWG_CASE(25) SWG_CASE(26) SWG_CASE(27) SWG_CASE(28) SWG_CASE(29) SWG_CASE(30) SWG_CASE(31) SWG_CASE(32)
+#undef SWG_CASE
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    if (p.gap_extend == 2) {            // gap-extend penalty as an immediate, any gap-open penalty (see wavefront.cuh)
+        switch (K) {
+#define SWG_CASE(k) case k: return launch_one<Lane16, 32, k, true, false, 0, 2>(grid, smem, stream, p);
+            SWG_CASE(1) SWG_CASE(2) SWG_CASE(3) SWG_CASE(4) SWG_CASE(5) SWG_CASE(6) SWG_CASE(7) SWG_CASE(8) SWG_CASE(9) SWG_CASE(10) SWG_CASE(11) SWG_CASE(12) SWG_CASE(13) SWG_CASE(14) SWG_CASE(15) SWG_CASE(16) SWG_CASE(17) SWG_CASE(18) SWG_CASE(19) SWG_CASE(20) SWG_CASE(21) SWG_CASE(22) SWG_CASE(23) SWG_CASE(24) SWG_CASE(25) SWG_CASE(26) SWG_CASE(27) SWG_CASE(28) SWG_CASE(29) SWG_CASE(30) SWG_CASE(31) SWG_CASE(32)
+#undef SWG_CASE
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (K) {
 #define SWG_CASE(k) case k: return launch_one<Lane16, 32, k, true, false>(grid, smem, stream, p);
         SWG_CASE(1) SWG_CASE(2) SWG_CASE(3) SWG_CASE(4) SWG_CASE(5) SWG_CASE(6) SWG_CASE(7) SWG_CASE(8)
