@@ -1,10 +1,13 @@
 // swg_api.cu -- the C ABI of libswimm_cuda.so (include/swimm_gpu.h): context, resident database,
 // query upload, kernel scheduling, top-r, statistics, and the reference-signature entry point.
 //
-// One context drives one GPU through one stream.  A search call enqueues, per query,
-//     profile build (K0)  ->  [long tiles: wavefront<Lane16, 32, KL>]  ->  wavefront<Lane16, G, K>  (K1)
-//                         ->  wavefront<Lane32, 32, KL> over the lanes that left the 16-bit range  (K2)
-// and once per batch the top-r selection (K4); nothing waits on the host until the results are fetched.
+// One context drives one GPU.  swg_gpu_run plans the batch (swg_plan.cu), then enqueues without waiting on the host:
+//     single queries      profile build (K0) -> wavefront<Lane16, G, K> (K1) -> 32-bit recomputation of its list (K2)
+//     groups of queries   per launch: pair profile -> wavefront_q2<G, K> (K1q); K2 when a query ends
+//     long tiles          split off per work item and run beside the main launches on the high-priority stream:
+//                         wavefront_xw (K3), or -- one-pass queries -- the 32-thread shape of K1 on column chunks
+//     per chunk of queries  top-r selection (K4)
+// swg_gpu_submit / swg_gpu_poll run the same with two query-buffer sets, so that two batches can be in flight.
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_xw_kernel(const Wf
     const uint2 *const ring_in = ring_out - R;        // the ring of the warp above (has_in)
     const uint32_t *const flag_prev = &s_prog[warp - (has_in ? 1 : 0)];
     const uint32_t *const flag_next = &s_prog[warp + (has_out ? 1 : 0)];
-    const reg nge = GOE > 0 ? L::splat(-GE) : L::splat(-p.gap_extend);
+    const reg nge = GE > 0 ? L::splat(-GE) : L::splat(-p.gap_extend);              // (immediates: see wavefront.cuh)
     const reg ngoe = GOE > 0 ? L::splat(-GOE) : L::splat(-p.gap_open_extend);
     const uint32_t pad_pk = (L::kSeqs == 2) ? 0x60006000u : 0x00006000u;
     const uint8_t *const prof = prof_smem + w * SLICE + (uint32_t)t * 16;
