@@ -111,9 +111,13 @@ struct swg_ctx {
     DeviceBuf d_scores, d_profile, d_profile32, d_boundary, d_counters, d_resc_list, d_topk_scratch, d_top_out;
     DeviceBuf d_profile_q2, d_lines, d_resc_list2, d_q2_counters;
     DeviceBuf d_profile_xw, d_xw_counters, d_xw_list;
-    DeviceBuf d_vt;                          // column-chunk tables of the long tiles (uint4 per chunk), all queries of a run
-    uint4 *h_vt = nullptr;                   // pinned staging of the same
-    size_t h_vt_cap = 0;
+    // column-chunk tables of the long tiles (uint4 per chunk), all queries of a run; two sets, used in turn, so that the
+    // next batch's tables can be staged while the running batch still reads its own (swg_gpu_submit)
+    DeviceBuf d_vt[2];
+    uint4 *h_vt[2] = {nullptr, nullptr};     // pinned staging of the same
+    size_t h_vt_cap[2] = {0, 0};
+    cudaEvent_t ev_vt[2] = {nullptr, nullptr};   // recorded behind the run that read set k
+    int vt_set = 0;
     int submat_max = 0;                      // largest entry of the current substitution matrix
     DeviceBuf d_q_off, d_align_lines, d_coords;                      // coordinate pass (align_ends.cu)     // long-sequence kernel (wavefront_xw.cuh)
     std::vector<WorkItem> items;            // schedule of the last run
@@ -398,8 +402,11 @@ void swg_gpu_destroy(swg_ctx *ctx)
     ctx->d_profile_xw.release();
     ctx->d_xw_counters.release();
     ctx->d_xw_list.release();
-    ctx->d_vt.release();
-    if (ctx->h_vt) cudaFreeHost(ctx->h_vt);
+    for (int k = 0; k < 2; ++k) {
+        ctx->d_vt[k].release();
+        if (ctx->h_vt[k]) cudaFreeHost(ctx->h_vt[k]);
+        if (ctx->ev_vt[k]) cudaEventDestroy(ctx->ev_vt[k]);
+    }
     ctx->d_q_off.release();
     ctx->d_align_lines.release();
     ctx->d_coords.release();
@@ -1008,19 +1015,22 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
         SWG_CUDA(ctx, ctx->d_resc_list2.reserve(std::max<uint64_t>(n_pad, 1) * sizeof(uint32_t)));
         SWG_CUDA(ctx, ctx->d_q2_counters.reserve((size_t)q2_launches * sizeof(uint32_t)));
     }
+    const int vset = ctx->vt_set;
     if (!vt_all.empty()) {
+        ctx->vt_set ^= 1;
         const size_t bytes = vt_all.size() * sizeof(uint4);
-        if (bytes > ctx->h_vt_cap) {
-            if (ctx->h_vt) cudaFreeHost(ctx->h_vt);
-            ctx->h_vt = nullptr;
-            ctx->h_vt_cap = 0;
-            SWG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_vt, 2 * bytes));
-            ctx->h_vt_cap = 2 * bytes;
+        if (!ctx->ev_vt[vset]) SWG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_vt[vset], cudaEventDisableTiming));
+        SWG_CUDA(ctx, cudaEventSynchronize(ctx->ev_vt[vset]));      // the run before last, which read this set, is over
+        if (bytes > ctx->h_vt_cap[vset]) {
+            if (ctx->h_vt[vset]) cudaFreeHost(ctx->h_vt[vset]);
+            ctx->h_vt[vset] = nullptr;
+            ctx->h_vt_cap[vset] = 0;
+            SWG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_vt[vset], 2 * bytes));
+            ctx->h_vt_cap[vset] = 2 * bytes;
         }
-        SWG_CUDA(ctx, ctx->d_vt.reserve(bytes));
-        SWG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // a previous run may still read the tables
-        memcpy(ctx->h_vt, vt_all.data(), bytes);
-        SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_vt.p, ctx->h_vt, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        SWG_CUDA(ctx, ctx->d_vt[vset].reserve(bytes));
+        memcpy(ctx->h_vt[vset], vt_all.data(), bytes);
+        SWG_CUDA(ctx, cudaMemcpyAsync(ctx->d_vt[vset].p, ctx->h_vt[vset], bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (any_xw) {
         SWG_CUDA(ctx, ctx->d_profile_xw.reserve((size_t)16 * kPassBytes));
@@ -1207,7 +1217,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
             uint64_t tasks = (uint64_t)x.tile_count * kTilePairs;
             if (vt_of[q].second) {
                 // column chunks instead of whole tiles (scores merged with atomicMax: zeroed in phase 0)
-                x.vt = ctx->d_vt.as<uint4>() + vt_of[q].first;
+                x.vt = ctx->d_vt[vset].as<uint4>() + vt_of[q].first;
                 x.vt_count = (uint32_t)vt_of[q].second;
                 tasks = (uint64_t)x.vt_count * kTilePairs;
             }
@@ -1463,6 +1473,7 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
     if (!ctx->ntiles && nq * top) SWG_CUDA(ctx, cudaMemsetAsync(ctx->d_top_out.p, 0, nq * top * sizeof(uint64_t), ctx->stream));
     SWG_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
     SWG_CUDA(ctx, cudaEventRecord(ctx->ev_bufs_free, ctx->stream));
+    if (!vt_all.empty()) SWG_CUDA(ctx, cudaEventRecord(ctx->ev_vt[vset], ctx->stream));
     ctx->run_done = true;
     return SWG_OK;
 }
