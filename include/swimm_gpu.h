@@ -146,6 +146,14 @@ int swg_gpu_get_query_kernels(swg_ctx *ctx, int32_t *kind, uint64_t max_queries)
 int swg_plan_describe(const uint16_t *q_lengths, uint64_t q_count, uint64_t n_sequences, uint64_t n_residues,
                       uint32_t longest_sequence, int query_pairing, char *text, uint64_t capacity);
 
+/* The column chunks swg_gpu_run cuts long tiles into for a query of m <= 1024 rows (pure host code, works without a
+ * GPU; what the exactness argument rests on is tested through this entry): tile_cols[n_tiles] = columns of every long
+ * tile (multiples of 8), smax = largest entry of the substitution matrix, option as "chunk_columns".  chunks receives
+ * up to `capacity` triples (tile, first column, columns), *n_chunks their number (0: no chunking), *span_bound the
+ * largest number of columns an alignment of the query can span. */
+int swg_plan_column_chunks(uint32_t m, int smax, int extend_gap, long option, const uint32_t *tile_cols, uint32_t n_tiles,
+                           uint32_t *chunks, uint64_t capacity, uint64_t *n_chunks, uint64_t *span_bound);
+
 /* Measured issue rates of the search kernel's instruction mix (the integer roofline the search is
  * reported against).  ginstr_per_s[p] = 1e9 thread-instructions per second on the whole GPU for probe p,
  * sm_mhz[p] = the SM clock during it, names[p] = static strings.  max_probes >= 64 is enough. */

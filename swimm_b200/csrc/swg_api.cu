@@ -918,32 +918,17 @@ int swg_gpu_run(swg_ctx *ctx, uint64_t top, int keep_scores)
                 XwConfig xc = choose_xw_config(m, pairs, long_cols * kTilePairs, (double)ctx->maxcols, lg, ctx->xw_warps, ctx->xw_rows);
                 if (m <= (uint32_t)kMaxPassRows && !ctx->xw_warps && !ctx->xw_rows) {
                     const int K = (int)((m + 31) / 32);
-                    // Column chunks.  An alignment with a positive score has fewer than m * Smax / ge database-only
-                    // columns (each costs at least ge, the matches earn at most m * Smax), so it spans at most
-                    // B = m + m * Smax / ge columns: chunks of C columns that overlap by B each contain every
-                    // alignment that starts in their first C - B columns, and a sequence's score is the best of its
-                    // chunks -- exactly.  For a short query B is far below a long sequence's length, and the chunks are
-                    // independent tasks: no serial chain is left.
+                    // (column chunks: swg_plan.cu, plan_column_chunks)
                     size_t n_chunks = 0;
-                    uint32_t C = 0, stride = 0;
-                    if (ctx->extend_gap >= 1 && ctx->submat_max >= 1 && ctx->chunk_columns != 1) {
-                        const uint64_t B = (uint64_t)m + (uint64_t)m * ctx->submat_max / ctx->extend_gap + 1;
-                        const uint64_t want = ctx->chunk_columns > 1 ? (uint64_t)ctx->chunk_columns : std::max<uint64_t>(2 * B, 2048);
-                        C = (uint32_t)std::min<uint64_t>((std::max(want, B + 8) + 7) / 8 * 8, 1u << 20);
-                        stride = (uint32_t)((C - B) / 8 * 8);
-                        if (stride >= 8 && (uint64_t)C * 2 <= ctx->maxcols) {
+                    uint32_t C = 0;
+                    {
+                        std::vector<ColumnChunk> chunks;
+                        C = plan_column_chunks(m, ctx->submat_max, ctx->extend_gap, ctx->chunk_columns, ctx->h_tile_cols.data(), fl,
+                                               ctx->ntiles, ctx->maxcols, chunks);
+                        if (!chunks.empty()) {
                             const size_t first = vt_all.size();
-                            for (uint32_t t = ctx->ntiles; t-- > fl;) {
-                                const uint32_t cols = ctx->h_tile_cols[t];
-                                if (cols <= C) { vt_all.push_back(make_uint4(t, 0, cols, 0)); continue; }
-                                for (uint32_t c0 = 0;; c0 += stride) {
-                                    const uint32_t len = std::min(C, cols - c0);
-                                    vt_all.push_back(make_uint4(t, c0, len, 0));
-                                    if (c0 + len >= cols) break;
-                                }
-                            }
-                            std::stable_sort(vt_all.begin() + first, vt_all.end(), [](const uint4 &a, const uint4 &b) { return a.z > b.z; });
-                            n_chunks = vt_all.size() - first;
+                            for (const ColumnChunk &c : chunks) vt_all.push_back(make_uint4(c.tile, c.col0, c.cols, 0));
+                            n_chunks = chunks.size();
                             vt_of[q] = std::make_pair(first, n_chunks);
                         }
                     }
@@ -1743,6 +1728,25 @@ int swg_plan_describe(const uint16_t *q_lengths, uint64_t q_count, uint64_t n_se
     const size_t n = std::min<size_t>(out.size(), (size_t)capacity - 1);
     memcpy(text, out.data(), n);
     text[n] = 0;
+    return SWG_OK;
+}
+
+int swg_plan_column_chunks(uint32_t m, int smax, int extend_gap, long option, const uint32_t *tile_cols, uint32_t n_tiles,
+                           uint32_t *chunks /* [capacity][3] = tile, first column, columns */, uint64_t capacity, uint64_t *n_chunks,
+                           uint64_t *span_bound)
+{
+    if (!n_chunks || (n_tiles && !tile_cols)) return fail(nullptr, SWG_ERR_ARG, "NULL argument");
+    uint32_t maxcols = 8;
+    for (uint32_t t = 0; t < n_tiles; ++t) maxcols = std::max(maxcols, tile_cols[t]);
+    std::vector<ColumnChunk> out;
+    plan_column_chunks(m, smax, extend_gap, option, tile_cols, 0, n_tiles, maxcols, out);
+    *n_chunks = out.size();
+    if (span_bound) *span_bound = alignment_span_bound(m, smax, extend_gap);
+    for (uint64_t i = 0; chunks && i < out.size() && i < capacity; ++i) {
+        chunks[3 * i] = out[i].tile;
+        chunks[3 * i + 1] = out[i].col0;
+        chunks[3 * i + 2] = out[i].cols;
+    }
     return SWG_OK;
 }
 

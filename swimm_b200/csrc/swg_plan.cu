@@ -207,6 +207,36 @@ XwConfig choose_xw_config(uint32_t m, double pairs, double pair_columns, double 
     return best;
 }
 
+uint64_t alignment_span_bound(uint32_t m, int smax, int ge)
+{
+    if (ge < 1 || smax < 1) return 0;
+    if (m == 0) m = 1;
+    return (uint64_t)m + (uint64_t)m * (uint64_t)smax / (uint64_t)ge + 1;
+}
+
+uint32_t plan_column_chunks(uint32_t m, int smax, int ge, long option, const uint32_t *tile_cols, uint32_t first_tile,
+                            uint32_t ntiles, uint32_t maxcols, std::vector<ColumnChunk> &out)
+{
+    out.clear();
+    const uint64_t B = alignment_span_bound(m, smax, ge);
+    if (B == 0 || option == 1) return 0;
+    const uint64_t want = option > 1 ? (uint64_t)option : std::max<uint64_t>(2 * B, 2048);
+    const uint32_t C = (uint32_t)std::min<uint64_t>((std::max(want, B + 8) + 7) / 8 * 8, 1u << 20);
+    const uint32_t stride = (uint32_t)((C - B) / 8 * 8);            // chunk starts stay multiples of 8 (the layout's column chunks)
+    if (stride < 8 || (uint64_t)C * 2 > maxcols) return 0;
+    for (uint32_t t = ntiles; t-- > first_tile;) {
+        const uint32_t cols = tile_cols[t];
+        if (cols <= C) { out.push_back({t, 0, cols}); continue; }
+        for (uint32_t c0 = 0;; c0 += stride) {
+            const uint32_t len = std::min(C, cols - c0);
+            out.push_back({t, c0, len});
+            if (c0 + len >= cols) break;
+        }
+    }
+    std::stable_sort(out.begin(), out.end(), [](const ColumnChunk &a, const ColumnChunk &b) { return a.cols > b.cols; });
+    return C;
+}
+
 // ---- the batch ------------------------------------------------------------------------------------
 void plan_batch(const std::vector<uint16_t> &q_len, const ShardShape &shard, const PlanOptions &opt,
                 std::vector<Config> &main_cfgs, std::vector<Config> &wide_cfgs, std::vector<WorkItem> &items)

@@ -89,6 +89,19 @@ double xw_rate(int K);
 XwConfig choose_xw_config(uint32_t m, double pairs, double pair_columns, double maxcols, int ctas, long force_warps = 0,
                           long force_rows = 0);
 
+// Column chunks of long tiles for a query of one pass (m <= 1024 rows).  An alignment with a positive score has fewer
+// than m * Smax / ge database-only columns (each costs at least ge, the aligned pairs earn at most m * Smax), so it spans
+// at most B = m + m * Smax / ge + 1 columns.  Chunks of C columns whose starts are (C - overlap) apart with overlap >= B
+// therefore contain every such alignment entirely in at least one chunk, and a sequence's score is the best score of
+// its chunks -- exactly; the chunks are independent tasks: no serial chain is left.
+struct ColumnChunk { uint32_t tile, col0, cols; };
+uint64_t alignment_span_bound(uint32_t m, int smax, int ge);       // B; 0 when there is no bound (ge < 1 or smax < 1)
+// tiles [first_tile, ntiles) with tile_cols[] columns each (multiples of 8) -> chunks, longest first.  option: 0 = chunk
+// length max(2B, 2048), 1 = off, > 1 = that many columns (at least B + 8).  Returns C, or 0 (and no chunks) when
+// chunking is off, unbounded, or would not at least halve the longest tile (2 C > maxcols).
+uint32_t plan_column_chunks(uint32_t m, int smax, int ge, long option, const uint32_t *tile_cols, uint32_t first_tile,
+                            uint32_t ntiles, uint32_t maxcols, std::vector<ColumnChunk> &out);
+
 // query-pair kernel: launch heights covering m rows; the two lanes as streams of queries
 PairConfig choose_pair_config(uint32_t m, long force_group, long force_rows);
 double plan_stream(const std::vector<uint32_t> lanes[2], const std::vector<uint16_t> &q_len, long force_rows,

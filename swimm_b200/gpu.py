@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "swg_gpu_set_queries", "swg_gpu_run", "swg_gpu_fetch", "swg_gpu_sync", "swg_gpu_get_stats", "swg_gpu_get_query_seconds",
     "swg_gpu_get_query_kernels", "swg_plan_describe", "swg_gpu_pipebench",
     "swg_gpu_set_option", "swg_gpu_debug_read", "swimm_gpu_search_avx2_compat", "swg_gpu_submit", "swg_gpu_poll",
-    "swg_gpu_load_db_offsets", "swg_gpu_align_ends",
+    "swg_gpu_load_db_offsets", "swg_gpu_align_ends", "swg_plan_column_chunks",
 ]
 
 
@@ -78,6 +78,7 @@ def load_library() -> C.CDLL:
     L.swg_gpu_debug_read.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     L.swg_gpu_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.swg_gpu_align_ends.argtypes = [vp, vp]
+    L.swg_plan_column_chunks.argtypes = [C.c_uint32, i32, i32, C.c_long, vp, C.c_uint32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.swg_gpu_submit.argtypes = [vp, vp, vp, vp, u64, vp, i32, i32, u64, C.POINTER(i32)]
     L.swg_gpu_poll.argtypes = [vp, i32, i32, vp, C.POINTER(C.c_double), C.POINTER(i32)]
     L.swimm_gpu_search_avx2_compat.argtypes = [vp, vp, C.c_ulong, vp, vp, vp, vp, C.c_ulong, vp, vp, i32, i32, i32, i32,
@@ -118,6 +119,19 @@ def plan_describe(q_lengths, n_sequences: int, n_residues: int, longest_sequence
     if st != 0:
         raise SwgError("swg_plan_describe -> %d: %s" % (st, L.swg_gpu_last_error(None).decode()))
     return buf.value.decode()
+
+
+def plan_column_chunks(m: int, smax: int, ge: int, tile_cols, option: int = 0):
+    """(chunks [n][3] = tile, first column, columns; span bound B) the library would use (host-only)."""
+    L = load_library()
+    tc = np.ascontiguousarray(tile_cols, dtype=np.uint32)
+    cap = int(tc.astype(np.int64).sum() // 8 + len(tc) + 8)
+    out = np.zeros((cap, 3), dtype=np.uint32)
+    n, b = C.c_uint64(0), C.c_uint64(0)
+    st = L.swg_plan_column_chunks(m, smax, ge, option, tc.ctypes.data, len(tc), out.ctypes.data, cap, C.byref(n), C.byref(b))
+    if st != 0:
+        raise SwgError("swg_plan_column_chunks -> %d" % st)
+    return out[:n.value], b.value
 
 
 class GpuSearch:

@@ -114,3 +114,39 @@ def test_random_batches_keep_the_invariants(seed):
                  longest_sequence=int(rng.integers(50, 40_000)))
     for pairing in (0, 1, 2):
         check_schedule(ql, gpu.plan_describe(ql, query_pairing=pairing, **shard))
+
+
+def test_column_chunks_cover_every_possible_alignment():
+    """The exactness of the column chunks rests on two host-side facts: the span bound B = m + m*Smax/ge + 1, and
+    that every window of at most B columns of a long tile lies entirely inside one chunk.  Checked on random tiles,
+    queries, matrices' maxima, penalties and chunk options; chunk starts are multiples of 8, chunks stay inside
+    their tile, together they cover it, and they come longest first."""
+    rng = np.random.default_rng(3)
+    for trial in range(300):
+        m = int(rng.integers(1, 1025))
+        smax = int(rng.integers(1, 18))
+        ge = int(rng.integers(1, 4))
+        option = int(rng.choice([0, 0, 0, 8, 1000, 2048, 5000, 20000]))
+        tiles = (rng.integers(1, 8192, int(rng.integers(1, 12))) * 8).astype(np.uint32)
+        chunks, B = gpu.plan_column_chunks(m, smax, ge, tiles, option)
+        assert B == m + m * smax // ge + 1
+        if len(chunks) == 0:
+            continue
+        assert (np.diff(chunks[:, 2].astype(np.int64)) <= 0).all()
+        for t, cols in enumerate(tiles):
+            mine = chunks[chunks[:, 0] == t]
+            mine = mine[np.argsort(mine[:, 1])]
+            assert len(mine) >= 1 and (mine[:, 1] % 8 == 0).all() and (mine[:, 1] + mine[:, 2] <= cols).all()
+            assert mine[0, 1] == 0 and mine[-1, 1] + mine[-1, 2] == cols
+            # every window [a, a + w) with w <= B inside the tile is inside some chunk: it suffices to check, for every
+            # chunk start s_k, that the window starting just before the NEXT chunk's start still fits into chunk k
+            starts, ends = mine[:, 1].astype(np.int64), (mine[:, 1] + mine[:, 2]).astype(np.int64)
+            for k in range(len(mine) - 1):
+                a = starts[k + 1] - 1                     # the last start that chunk k + 1 does not cover
+                assert min(a + B, cols) <= ends[k], (m, smax, ge, option, cols, mine)
+    # option 1 switches chunking off; a matrix or penalty without a bound does too
+    assert len(gpu.plan_column_chunks(144, 11, 2, [40000], 1)[0]) == 0
+    none, unbounded = gpu.plan_column_chunks(144, 11, 0, [40000], 0)
+    assert len(none) == 0 and unbounded == 0
+    chunks, B = gpu.plan_column_chunks(144, 11, 2, [40000], 0)
+    assert B == 937 and chunks[0, 2] == 2048 and len(chunks) > 30
