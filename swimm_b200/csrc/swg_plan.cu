@@ -133,6 +133,12 @@ double plan_stream(const std::vector<uint32_t> lanes[2], const std::vector<uint1
         uint32_t seg = std::min(rem[0], rem[1]);
         const uint32_t far = std::max(rem[0], rem[1]);
         if (far != 0xffffffffu && far - seg <= 192) seg = far;       // ends this close finish in the same launches
+        // the lane whose query ends first has nothing after it: its tail is idle whatever happens, so no launch
+        // boundary (and no short, slow launch) is spent on that end
+        if (far != 0xffffffffu && seg != far) {
+            const int ls = rem[0] <= rem[1] ? 0 : 1;
+            if (pos[ls] + 1 >= lanes[ls].size()) seg = far;
+        }
         const PairConfig pc = choose_pair_config(seg, 32, force_rows);
         bool fin[2] = {false, false};
         for (int K : pc.K) {
