@@ -366,8 +366,22 @@ void plan_batch(const std::vector<uint16_t> &q_len, const ShardShape &shard, con
         };
         if (opt.query_pairing && nq >= 2 && shard.ntiles) {
             // where the streams end and the single-pass pairs begin is a planner choice too
+            // candidates: a few fixed thresholds, and just below every (distinct) query length of at most one pass --
+            // i.e. the possible splits of the batch into streamed and paired queries
+            std::vector<uint32_t> cands = {(uint32_t)kMaxPassRows, 832u, 640u, 448u, 256u, 0u};
+            {
+                std::vector<uint32_t> lens;
+                for (uint64_t q = 0; q < nq; ++q)
+                    if (q_len[q] >= 1 && q_len[q] <= kMaxPassRows) lens.push_back((uint32_t)q_len[q] - 1);
+                std::sort(lens.begin(), lens.end());
+                lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
+                // (planning time grows with the batch: up to 16 extra candidates for batches of up to 64 queries, 8 beyond)
+                const size_t step = std::max<size_t>(1, (lens.size() + (nq <= 64 ? 15 : 7)) / (nq <= 64 ? 16 : 8));
+                for (size_t i = 0; i < lens.size(); i += step)
+                    if (std::find(cands.begin(), cands.end(), lens[i]) == cands.end()) cands.push_back(lens[i]);
+            }
             double best = 1e300;
-            for (uint32_t above : {(uint32_t)kMaxPassRows, 832u, 640u, 448u, 256u, 0u}) {
+            for (uint32_t above : cands) {
                 std::vector<WorkItem> cand;
                 const double c = build(above, cand);
                 if (c < best) { best = c; items.swap(cand); }
