@@ -274,12 +274,23 @@ void plan_batch(const std::vector<uint16_t> &q_len, const ShardShape &shard, con
         };
         auto single_cost = [&](uint32_t q) {
             const Config &c = main_cfgs[q];
-            return std::max((double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes) * res9, chain_seconds(c.K, c.passes));
+            return std::max((double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes) * res9, chain_seconds(c.K, c.passes)) + 20e-6;
         };
+        // (per launch also: the profile build, the launch gap and the tail, about 20 us; and -- when one lane continues a
+        // query while the other starts one or idles -- the pass over the lines that clears the other lane's half,
+        // 16 bytes per database column at about 7 TB/s)
+        const double clear_seconds = (double)shard.residues * 16.0 / 7.0e12;
         auto q2_cost = [&](const std::vector<Q2Launch> &ls) {
             double t = 0.0;
-            for (const Q2Launch &L : ls)
-                t += std::max(2.0 * L.G * L.K / q2_rate(L.G, L.K, ls.size() > 1) * res9, chain_seconds(L.K, 1));
+            for (const Q2Launch &L : ls) {
+                t += std::max(2.0 * L.G * L.K / q2_rate(L.G, L.K, ls.size() > 1) * res9, chain_seconds(L.K, 1)) + 20e-6;
+                bool continues = false, other = false;
+                for (int l = 0; l < 2; ++l) {
+                    if (L.lane[l].q >= 0 && !L.lane[l].first) continues = true;
+                    else other = true;
+                }
+                if (continues && other) t += clear_seconds;
+            }
             return t;
         };
         // One candidate schedule: queries longer than `stream_above` rows go to the two streams, the others are

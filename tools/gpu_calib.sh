@@ -1,8 +1,9 @@
 #!/bin/bash
-# Calibration of the planner's rate tables (both kernels) on the GPU box; then tools/make_rates.py here.
+# Calibration of the planner's rate tables (all three search kernels) on the GPU box; then, here:
+#   python tools/make_rates.py gpurun_out/r2/calib.json gpurun_out/r2/calib_q2.json gpurun_out/r2/calib_xw.json
 cd "$(dirname "$0")/.."
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_query_pairs.py -m gpu -q -x > gpurun_out/pytest_q2.log 2>&1; echo "pytest q2 exit $?"; tail -n 3 gpurun_out/pytest_q2.log
-timeout 900 python tools/calibrate_q2.py 0.35 > gpurun_out/calib_q2.json 2> gpurun_out/calib_q2.err; echo "calib q2 exit $?"
-timeout 900 python tools/calibrate.py 0.35 > gpurun_out/calib.json 2> gpurun_out/calib.err; echo "calib exit $?"
-tail -n 2 gpurun_out/calib_q2.err gpurun_out/calib.err
+O=gpurun_out/r2; mkdir -p $O
+timeout 900 python tools/calibrate_q2.py 0.35 > $O/calib_q2.json 2> $O/calib_q2.err; echo "calib q2 exit $?"
+timeout 900 python tools/calibrate.py 0.35 > $O/calib.json 2> $O/calib.err; echo "calib exit $?"
+timeout 900 python tools/calibrate_xw.py 4000 4,8,16 > $O/calib_xw.json 2> $O/calib_xw.err; echo "calib xw exit $?"
+tail -n 2 $O/calib_q2.err $O/calib.err $O/calib_xw.err
