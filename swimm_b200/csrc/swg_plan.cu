@@ -274,23 +274,12 @@ void plan_batch(const std::vector<uint16_t> &q_len, const ShardShape &shard, con
         };
         auto single_cost = [&](uint32_t q) {
             const Config &c = main_cfgs[q];
-            return std::max((double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes) * res9, chain_seconds(c.K, c.passes)) + 20e-6;
+            return std::max((double)c.passes * c.G * c.K / shape_rate(c.G, c.K, c.passes) * res9, chain_seconds(c.K, c.passes));
         };
-        // (per launch also: the profile build, the launch gap and the tail, about 20 us; and -- when one lane continues a
-        // query while the other starts one or idles -- the pass over the lines that clears the other lane's half,
-        // 16 bytes per database column at about 7 TB/s)
-        const double clear_seconds = (double)shard.residues * 16.0 / 7.0e12;
         auto q2_cost = [&](const std::vector<Q2Launch> &ls) {
             double t = 0.0;
-            for (const Q2Launch &L : ls) {
-                t += std::max(2.0 * L.G * L.K / q2_rate(L.G, L.K, ls.size() > 1) * res9, chain_seconds(L.K, 1)) + 20e-6;
-                bool continues = false, other = false;
-                for (int l = 0; l < 2; ++l) {
-                    if (L.lane[l].q >= 0 && !L.lane[l].first) continues = true;
-                    else other = true;
-                }
-                if (continues && other) t += clear_seconds;
-            }
+            for (const Q2Launch &L : ls)
+                t += std::max(2.0 * L.G * L.K / q2_rate(L.G, L.K, ls.size() > 1) * res9, chain_seconds(L.K, 1));
             return t;
         };
         // One candidate schedule: queries longer than `stream_above` rows go to the two streams, the others are
@@ -377,22 +366,8 @@ void plan_batch(const std::vector<uint16_t> &q_len, const ShardShape &shard, con
         };
         if (opt.query_pairing && nq >= 2 && shard.ntiles) {
             // where the streams end and the single-pass pairs begin is a planner choice too
-            // candidates: a few fixed thresholds, and just below every (distinct) query length of at most one pass --
-            // i.e. the possible splits of the batch into streamed and paired queries
-            std::vector<uint32_t> cands = {(uint32_t)kMaxPassRows, 832u, 640u, 448u, 256u, 0u};
-            {
-                std::vector<uint32_t> lens;
-                for (uint64_t q = 0; q < nq; ++q)
-                    if (q_len[q] >= 1 && q_len[q] <= kMaxPassRows) lens.push_back((uint32_t)q_len[q] - 1);
-                std::sort(lens.begin(), lens.end());
-                lens.erase(std::unique(lens.begin(), lens.end()), lens.end());
-                // (planning time grows with the batch: up to 16 extra candidates for batches of up to 64 queries, 8 beyond)
-                const size_t step = std::max<size_t>(1, (lens.size() + (nq <= 64 ? 15 : 7)) / (nq <= 64 ? 16 : 8));
-                for (size_t i = 0; i < lens.size(); i += step)
-                    if (std::find(cands.begin(), cands.end(), lens[i]) == cands.end()) cands.push_back(lens[i]);
-            }
             double best = 1e300;
-            for (uint32_t above : cands) {
+            for (uint32_t above : {(uint32_t)kMaxPassRows, 832u, 640u, 448u, 256u, 0u}) {
                 std::vector<WorkItem> cand;
                 const double c = build(above, cand);
                 if (c < best) { best = c; items.swap(cand); }
