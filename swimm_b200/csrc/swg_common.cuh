@@ -70,9 +70,8 @@ constexpr int kOverflow16 = 32000;           // a 16-bit lane whose best reaches
 // ---- query-pair kernel (wavefront_q2.cuh): 32-bit profile entries, per-sequence pass lines ----------
 constexpr int kQ2LetterStride = 4096;                       // 1024 rows x 4 bytes
 constexpr int kQ2ProfileBytes = kLetters * kQ2LetterStride; // one pass: 100 KB
-constexpr int kQ2MinSegCols = 48;                           // every segment is padded to at least this many columns (G = 32)
+constexpr int kQ2MinSegCols = 80;                           // every segment is padded to at least this many columns (G = 32: 2 x 32 + 16)
 constexpr int kQ2LineSlack = 8;                             // columns a line extends past its segment (prefetch overrun)
-constexpr uint32_t kQ2MarkSegment = 1u;                     // bit 0 of a column word: first column of a sequence
 
 struct WfParams {
     const uint4 *db;              // tiled database, 16-byte units

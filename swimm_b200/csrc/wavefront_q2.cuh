@@ -35,6 +35,14 @@ namespace swg {
 
 // G threads x K rows (K even); CIN: a lane's rows continue from the line of the previous launch; COUT: the last
 // row is parked for the next launch; GOE/GE > 0: gap penalties as immediates.
+//
+// A STEP IS TWO COLUMNS.  Thread t works two columns behind thread t-1, receives the (H, F) of the row above for both
+// columns in one round of shuffles, and walks the rows of the two columns interleaved -- row x of the first, then row
+// x-1 of the second.  The two walks are independent dependency chains (the second needs only E and the diagonal term of
+// the row the first has just finished), so the fixed latency of max3 -> add -> addmax of one chain is covered by the
+// other inside the same warp (ncu, one chain per step: 32 % of a warp's cycles in stall_wait, ALU pipe 84.5 % busy).
+// Thread 0's inputs are selects (one SEL each: measured 0.9 % faster than an IMAD pair that keeps them off the ALU
+// pipe -- an IMAD costs the ALU pipe about half a slot, pipebench pair_viaddmnmx_imad).
 template <int G, int K, bool CIN, bool COUT, int GOE, int GE>
 __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const WfParams p)
 {
@@ -46,8 +54,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
     constexpr int TPT = kTileSeqs / GPW;              // warp tasks per tile: every group takes one sequence
     constexpr int KCH = (K + 3) / 4;                  // 4-row (16-byte) profile chunks per thread
     constexpr int NC = kTripCols;
-    constexpr uint32_t FI = G / NC;
+    constexpr int SPT = NC / 2;                       // steps per trip
+    constexpr int SKEW = 2 * G;                       // columns between the words entering thread 0 and the rows leaving thread G-1
+    constexpr uint32_t FI = SKEW / NC;                // head trips: thread G-1 is still on the previous segment
     constexpr uint32_t kMinTrips = FI + 4;
+    static_assert(NC == 4, "two steps of two columns per trip");
     static_assert(kMinTrips * NC <= kQ2MinSegCols, "line stride too short for padded segments");
 
     extern __shared__ __align__(16) uint8_t prof_smem[];
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
     // (second operand of a VIADD.16x2: no difference in rate, kept for SWIMM's defaults)
     const reg nge = GE > 0 ? L::splat(-GE) : L::splat(-p.gap_extend);
     const reg ngoe = GOE > 0 ? L::splat(-GOE) : L::splat(-p.gap_open_extend);
-    const uint32_t pad_pk = 0x00006000u;
+    const uint32_t pad_pk = 0x60000060u;                         // two pad letters (see the step's word below)
     const uint32_t ntasks = p.tile_count * TPT;
     // a line nobody reads: where the flush segments (and the kernel's first head steps) park their rows
     uint2 *const dummy_line = p.boundary + p.line_dummy + (size_t)(warp_global * GPW + g) * (kQ2MinSegCols + kQ2LineSlack);
@@ -87,58 +98,76 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
 #pragma unroll
     for (int x = 0; x < K; ++x) { DS[x] = L::splat(0); E[x] = L::splat(0); }
     reg best = L::splat(0), bsave = L::splat(0);
-    reg out_h = L::splat(0), out_f = L::splat(0);
+    reg out_ha = L::splat(0), out_fa = L::splat(0), out_hb = L::splat(0), out_fb = L::splat(0);
     uint32_t pk = pad_pk;
     const uint32_t slice_off = (uint32_t)t * 16;
-    uint32_t first_mask = t == 0 ? 0xffffffffu : 0u;            // all ones in the thread that feeds the pipeline
-    asm volatile("" : "+r"(first_mask));                         // opaque: keeps the blends below from turning back into selects
+    const bool is_first = t == 0;                                // the thread that feeds the pipeline
 
-    // One step: process the column whose word arrived in the previous step with the (H, F) of the row above handed
-    // down now, and form DS for the column whose word arrives now (see wavefront.cuh).  HEAD steps (the first G of
-    // a segment) look at the segment mark; steady-state steps do not.
-    auto column = [&](auto head_tag, uint32_t in_pkn, uint2 in_hf, uint2 *store_to) {
-        constexpr bool HEAD = decltype(head_tag)::value;
+    // One step: process the two columns (a, b) whose letters arrived in the previous step with the (H, F) of the row
+    // above handed down now, and form DS for b and for the a of the next step from the letters that arrive now (see
+    // wavefront.cuh).  The step's word: byte 0 = letter of b, byte 3 = letter of the next a, both as code * 4.
+    // restart: the next a is the first column of a new sequence (head steps only: thread t meets it in step t).
+    auto step = [&](uint32_t in_pk, uint2 in_a, uint2 in_b, uint2 *store_to, bool restart) {
         uint32_t pkn = __shfl_up_sync(0xffffffffu, pk, 1, G);
-        reg r_h = __shfl_up_sync(0xffffffffu, out_h, 1, G);
-        reg r_f = __shfl_up_sync(0xffffffffu, out_f, 1, G);
-        // thread 0 takes the entering column word and the (H, F) above row 0 instead: a mask blend (one LOP3 each,
-        // no predicate to keep alive across the row loop)
-        pkn ^= (pkn ^ in_pkn) & first_mask;
-        r_h = CIN ? (r_h ^ ((r_h ^ in_hf.x) & first_mask)) : (r_h & ~first_mask);
-        r_f = CIN ? (r_f ^ ((r_f ^ in_hf.y) & first_mask)) : (r_f & ~first_mask);
+        reg r_ha = __shfl_up_sync(0xffffffffu, out_ha, 1, G);
+        reg r_fa = __shfl_up_sync(0xffffffffu, out_fa, 1, G);
+        reg r_hb = __shfl_up_sync(0xffffffffu, out_hb, 1, G);
+        reg r_fb = __shfl_up_sync(0xffffffffu, out_fb, 1, G);
+        if (is_first) {
+            pkn = in_pk;
+            r_ha = CIN ? in_a.x : 0u; r_fa = CIN ? in_a.y : 0u;
+            r_hb = CIN ? in_b.x : 0u; r_fb = CIN ? in_b.y : 0u;
+        }
         pk = pkn;
 
-        // packed scores of the NEXT column: letter offset code*4096 (the word carries code*4 in byte lane 1).  The
-        // 16-byte loads are consumed chunk by chunk inside the row loop (short live ranges: K <= 32 rows fit in 128
-        // registers); the rare segment restart below reads them again instead of keeping them alive.
-        const uint4 *q = reinterpret_cast<const uint4 *>(prof_smem + (((pkn & 0xff00u) << 2) | slice_off));
-        reg hp = r_h, f = r_f, dsprev = L::splat(0);
+        // packed scores of the following columns: letter offset code * 4096.  pkn * 1024 drops byte 3 from the 32-bit
+        // product; pkn >> 14 = byte 3 * 1024.  The 16-byte loads are consumed chunk by chunk inside the row loop (short
+        // live ranges); the rare segment restart below reads them again.
+        const uint4 *qa = reinterpret_cast<const uint4 *>(prof_smem + (pkn * 1024u + slice_off));
+        const uint4 *qb = reinterpret_cast<const uint4 *>(prof_smem + ((pkn >> 14) + slice_off));
+        reg hpa = r_ha, fa = r_fa, dspa = L::splat(0);
+        reg hpb = r_hb, fb = r_fb, dspb = L::splat(0);
+        uint4 va = make_uint4(0u, 0u, 0u, 0u), vb = va;
 #pragma unroll
-        for (int i = 0; i < KCH; ++i) {
-            const uint4 v = q[i * G];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int x = 4 * i + k;
-                if (x >= K) continue;                          // K = 4n + 2: the last chunk is half used
-                const uint32_t wx = k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w;
+        for (int x = 0; x <= K; ++x) {
+            if (x < K) {                                       // row x of column a
+                if (x % 4 == 0) va = qa[(x / 4) * G];
+                const uint32_t wx = x % 4 == 0 ? va.x : x % 4 == 1 ? va.y : x % 4 == 2 ? va.z : va.w;
                 const reg ds = DS[x];
-                const reg h = L::max3_relu(ds, E[x], f);       // max(ds, E(i,j), F(i,j), 0)
+                const reg h = L::max3_relu(ds, E[x], fa);      // max(ds, E(i,j), F(i,j), 0)
                 const reg open = L::add(h, ngoe);              // H(i,j) - (go+ge)
                 E[x] = L::addmax(E[x], nge, open);             // E(i,j+1)
-                f = L::addmax(f, nge, open);                   // F(i+1,j)
-                if (x & 1) best = L::max3(best, dsprev, ds);
-                dsprev = ds;
-                DS[x] = L::add(hp, wx);                        // H(i-1,j) + S(i,j+1)
-                hp = h;
+                fa = L::addmax(fa, nge, open);                 // F(i+1,j)
+                if (x & 1) best = L::max3(best, dspa, ds);
+                dspa = ds;
+                DS[x] = L::add(hpa, wx);                       // H(i-1,j) + S(i,j+1)
+                hpa = h;
+            }
+            if (x >= 1) {                                      // row x-1 of column b
+                const int y = x - 1;
+                if (y % 4 == 0) vb = qb[(y / 4) * G];
+                const uint32_t wy = y % 4 == 0 ? vb.x : y % 4 == 1 ? vb.y : y % 4 == 2 ? vb.z : vb.w;
+                const reg ds = DS[y];
+                const reg h = L::max3_relu(ds, E[y], fb);
+                const reg open = L::add(h, ngoe);
+                E[y] = L::addmax(E[y], nge, open);
+                fb = L::addmax(fb, nge, open);
+                if (y & 1) best = L::max3(best, dspb, ds);
+                dspb = ds;
+                DS[y] = L::add(hpb, wy);
+                hpb = h;
             }
         }
-        out_h = hp;
-        out_f = f;
-        if (COUT && t == G - 1) __stcs(store_to, make_uint2(out_h, out_f));
-        if (HEAD && (pkn & kQ2MarkSegment)) {          // the next column starts a new sequence
+        out_ha = hpa; out_fa = fa;
+        out_hb = hpb; out_fb = fb;
+        if (COUT && t == G - 1) {
+            __stcs(store_to, make_uint2(out_ha, out_fa));
+            __stcs(store_to + 1, make_uint2(out_hb, out_fb));
+        }
+        if (restart) {                                 // the next column starts a new sequence
 #pragma unroll
             for (int i = 0; i < KCH; ++i) {
-                const uint4 v = q[i * G];
+                const uint4 v = qb[i * G];
                 DS[4 * i] = v.x; DS[4 * i + 1] = v.y;
                 if (4 * i + 2 < K) { DS[4 * i + 2] = v.z; DS[4 * i + 3] = v.w; }
             }
@@ -179,10 +208,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
     bool pending = false;
     uint32_t pend_lseq = 0;
     uint32_t next_task = fetch_task();
-    uint2 hf_in = make_uint2(0u, 0u);
-    // thread G-1 runs G columns behind the words: during the head steps of a segment it is still parking columns of
-    // the PREVIOUS segment.  st_cur[s] / st_prev[s] = where the row processed in step s of the current segment goes.
-    uint2 *st_cur = dummy_line + kQ2MinSegCols - G;     // as if a flush segment had just ended
+    uint2 hf_in0 = make_uint2(0u, 0u), hf_in1 = make_uint2(0u, 0u);
+    uint32_t wlast = kPadWord;                           // the last two columns of the previous trip (thread 0)
+    // thread G-1 runs SKEW columns behind the words: during the head steps of a segment it is still parking columns of
+    // the PREVIOUS segment.  st_cur[c] / st_prev[c] = where the rows leaving in the step that takes in column c go.
+    uint2 *st_cur = dummy_line + kQ2MinSegCols - SKEW;     // as if a flush segment had just ended
 
     for (;;) {
         const uint32_t task = next_task;
@@ -208,39 +238,51 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
         const uint32_t data_trips = ncols / NC;
         const uint32_t trips = data_trips < kMinTrips ? kMinTrips : data_trips;
         const uint32_t seg_cols = trips * NC;
-        const uint32_t selA = 0x7604u | (half << 4);              // residue byte of this sequence -> byte lane 1
-        const uint32_t selB = 0x7604u | ((2u + half) << 4);
+        // the step's word from two consecutive 4-byte words of the sequence pair (2 columns x 2 sequences each): byte 0 =
+        // this sequence's residue in the second column of the first word, byte 3 = in the first column of the second
+        // word, bytes 1 and 2 = 0 (sign replication of a byte below 128)
+        const uint32_t sel = 0x0882u | half | ((4u + half) << 12);
         uint2 *const st_prev = st_cur;                            // st_cur of the previous segment + its column count
-        st_cur = line - G;
+        st_cur = line - SKEW;
 
         uint2 w = make_uint2(kPadWord, kPadWord);
         if (t == 0 && data_trips > 0) w = words[0];
-        uint2 ring[NC];
+        uint2 ring[NC];                                           // ring[j]: (H, F) above row 0 for column c0 + j - 2
 #pragma unroll
         for (int j = 0; j < NC; ++j) ring[j] = make_uint2(0u, 0u);
         if (CIN) {
-            ring[0] = hf_in;
+            ring[0] = hf_in0;
+            ring[1] = hf_in1;
             if (t == 0 && have) {
-#pragma unroll
-                for (int j = 1; j < NC; ++j) ring[j] = __ldcs(line + j - 1);
+                ring[2] = __ldcs(line);
+                ring[3] = __ldcs(line + 1);
             }
         }
         auto trip_body = [&](auto head_tag, uint32_t trip) {
             constexpr bool HEAD = decltype(head_tag)::value;
+            // the words of the next trip, as two 4-byte loads: an 8-byte load wants a register pair, w.y moves on to wlast,
+            // and the copy out of the pair that ptxas then places right behind the load waits for the whole latency
             uint2 nw = make_uint2(kPadWord, kPadWord);
             const uint32_t nt = trip + 1;
-            if (t == 0 && nt < data_trips) nw = words[(nt >> 1) * (kTilePairs * 2) + (nt & 1u)];
+            if (t == 0 && nt < data_trips) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(words + ((nt >> 1) * (kTilePairs * 2) + (nt & 1u)));
+                nw.x = __ldg(src);
+                nw.y = __ldg(src + 1);
+            }
             const uint32_t c0 = trip * NC;
             uint2 *const st = (HEAD ? st_prev : st_cur) + c0;
 #pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                const uint32_t word = (j < 2) ? w.x : w.y;
-                const bool first = HEAD && j == 0 && trip == 0;
-                const uint32_t pkn = prmt(word, first ? kQ2MarkSegment : 0u, (j & 1) ? selB : selA);
-                const uint2 hf = CIN ? ring[j] : make_uint2(0u, 0u);
-                if (CIN && t == 0 && have) ring[j] = __ldcs(line + c0 + j + (NC - 1));
-                column(head_tag, pkn, hf, st + j);
+            for (int j = 0; j < SPT; ++j) {
+                const uint32_t pkn = j == 0 ? prmt(wlast, w.x, sel) : prmt(w.x, w.y, sel);
+                const uint2 hfa = CIN ? ring[2 * j] : make_uint2(0u, 0u);
+                const uint2 hfb = CIN ? ring[2 * j + 1] : make_uint2(0u, 0u);
+                if (CIN && t == 0 && have) {
+                    ring[2 * j] = __ldcs(line + c0 + 2 * j + 2);
+                    ring[2 * j + 1] = __ldcs(line + c0 + 2 * j + 3);
+                }
+                step(pkn, hfa, hfb, st + 2 * j, HEAD && trip * SPT + j == (uint32_t)t);
             }
+            wlast = w.y;
             w = nw;
         };
 #pragma unroll 1
@@ -252,7 +294,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) wavefront_q2_kernel(const Wf
             if (trip == fetch_trip) next_task = fetch_task();
             trip_body(steady_steps, trip);
         }
-        if (CIN) hf_in = ring[0];
+        if (CIN) { hf_in0 = ring[0]; hf_in1 = ring[1]; }
+        // the next segment reads the carried word with ITS selector (the other sequence of the pair, or another pair):
+        // leave this sequence's last residue in every byte
+        wlast = prmt(wlast, wlast, 0x2222u | (half * 0x1111u));
         st_cur += seg_cols;                                       // the next segment's head steps continue this line
         if (have) { pending = true; pend_lseq = lseq; }
     }
