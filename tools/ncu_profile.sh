@@ -13,11 +13,12 @@ $CMD > $O/prof3_plain.json 2> $O/prof3_plain.err || exit 1
 i=0
 for pat in "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.0, .bool.1" "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.1, .bool.1" "wavefront_q2_kernel<.int.32, .int.[0-9]+, .bool.1, .bool.0" "wavefront_kernel<swg::Lane16, .int.8, "; do
   i=$((i+1)); SKIP=10; if [ $i = 4 ]; then SKIP=3; fi
-  if [ -n "$ONLY" ] && [ "$ONLY" != "$i" ]; then continue; fi
+  if [ -n "$ONLY" ] && ! echo " $ONLY " | grep -q " $i "; then continue; fi
   # the first launches of every instantiation are the empty warm-up launches of the first run: skip past them
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"$pat" -s $SKIP -c 1 -f -o $O/prof3_$i $CMD > $O/ncu3_$i.log 2>&1
   echo "capture $i exit $?"
 done
+if [ -n "$ONLY" ] && ! echo " $ONLY " | grep -q " 5 "; then ls -la $O | grep prof3; exit 0; fi
 CMD="python tools/xw_profile_target.py"
 $CMD > $O/xw_plain.txt 2>&1 || exit 1
 tail -n 3 $O/xw_plain.txt
