@@ -247,3 +247,34 @@ def test_pairs_degenerate_inputs(gpu):
     sc, keys = gpu.search(np.array([5, 6], np.int8), np.array([1, 1], np.uint16), np.array([0, 1], np.uint32), b62, 10, 2, 3,
                           want_scores=True)
     assert sc.shape == (2, 0) and (keys == 0).all()
+
+
+@pytest.mark.parametrize("shape", [(32, 8), (32, 30), (16, 10), (8, 8)])
+def test_full_length_sequences_last_residue_across_segment_boundaries(gpu, oracle, forced, shape):
+    """Every sequence fills its tile's columns to the last one (lengths are multiples of 8, equal inside a tile, so no
+    padding separates consecutive sequences) and ends with a copy of a query's tail: the last residue of a sequence
+    reaches thread 0 in the first step of the NEXT sequence (the other one of the pair, or another pair) and must
+    still be read as this sequence's residue.  One CTA, so that every group runs many sequences back to back."""
+    rng = np.random.default_rng(77 + shape[1])
+    q = synth.make_queries(rng, [90, 150, 700, 1300])
+    lens = np.repeat(np.array([88, 96, 96, 160, 168, 400, 408, 1024]), 16)
+    db = synth.make_seqset(rng, lens)
+    for t in range(db.n):
+        qi = int(rng.integers(q.n))
+        tail = q.seq(qi)[-min(60, int(lens[t])):]
+        db.residues[db.offsets[t + 1] - len(tail):db.offsets[t + 1]] = tail
+    _, dl, dc = synth.length_sorted(db)
+    _, ql, qc = synth.length_sorted(q)
+    do = np.zeros(db.n + 1, np.uint64)
+    np.cumsum(dl.astype(np.uint64), out=do[1:])
+    qo = np.zeros(q.n + 1, np.uint32)
+    np.cumsum(ql.astype(np.uint32), out=qo[1:])
+    want = oracle.search(qc, qo, dc, do, host.submat("blosum62"), 10, 2)
+    gpu.load_db(dl, dc)
+    forced(*shape)
+    gpu.set_option("grid_blocks", 1)
+    try:
+        got, _ = gpu.search(qc, ql, qo[:-1], host.submat("blosum62"), 10, 2, 0, want_scores=True)
+    finally:
+        gpu.set_option("grid_blocks", 0)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:8]
