@@ -20,7 +20,10 @@ namespace swg {
 
 namespace {
 
-constexpr int kChains = 8;        // independent chains per thread (latency 4-6 cycles, 4 warps per scheduler)
+#ifndef SWG_PIPEBENCH_CHAINS
+#define SWG_PIPEBENCH_CHAINS 8
+#endif
+constexpr int kChains = SWG_PIPEBENCH_CHAINS;   // independent chains per thread (latency 4-6 cycles, 4 warps per scheduler)
 constexpr int kThreads = 512;
 constexpr int kBlocksPerSm = 1;
 constexpr int kUnroll = 16;      // cells per chain per loop trip (loop overhead < 2 %)
